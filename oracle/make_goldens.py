@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, CPU, fp32) on the deterministic synthetic weights of gpt-sovits_b200/synthetic.py.
+
+Run in the build container only:   python -m oracle.make_goldens
+The GPU box has no /root/reference; it checks the CUDA path and the numpy oracle against these files.
+
+Cases (weights are regenerated from the recorded seed, not stored):
+  naive_b1      infer_panel (= infer_panel_naive, t2s_model.py:814), B=1, 80 phonemes + 150 prompt,
+                greedy top_k=1, rp 1.35, early_stop_num=40: per-step logits, y, idx
+  batch_b4      infer_panel_batch_infer (:583), ragged B=4 (60/80/72/80 phonemes), P=150, greedy,
+                early_stop_num=24: per-step logits [n_active,1025], y_list, idx_list
+  retire_b6     infer_panel_batch_infer with an EOS-prone head (eos_scale=1.4): sequences retire at
+                different steps; y_list, idx_list, per-step logits
+  reffree_b1    infer_panel_naive with prompts=None (:849-856): y, idx(=0), logits
+  sampler_kat   logits_to_probs (utils.py:147) on hand-built rows: penalty sign flip, prompt
+                duplicates, top-k ties, top-p boundary, temperature clamp
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import gpt_sovits_b200  # noqa: E402  (alias loader)
+from gpt_sovits_b200 import synthetic  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _run(model, fn_name, args, kwargs):
+    hook = ref_harness.SampleHook().install()
+    try:
+        with ref_harness.quiet(), torch.no_grad():
+            y, idx = getattr(model, fn_name)(*args, **kwargs)
+    finally:
+        hook.remove()
+    return y, idx, hook
+
+
+def _pad_logits(lst):
+    """Steps have 1024 or 1025 columns and a shrinking number of rows -> pad with NaN."""
+    n = max(t.shape[0] for t in lst)
+    out = np.full((len(lst), n, 1025), np.nan, np.float32)
+    for s, t in enumerate(lst):
+        out[s, : t.shape[0], : t.shape[1]] = t.numpy()
+    return out
+
+
+def case_naive_b1(model):
+    ids, lens, prompt, bert = synthetic.make_inputs(1, [80], 150, seed=1)
+    y, idx, hook = _run(model, "infer_panel",
+                        (ids[0][None], lens, prompt, bert[0][None]),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=40, repetition_penalty=1.35))
+    # NOTE: hook.logits are post-penalty because the reference penalises in place (utils.py:167) and
+    # the hook clones BEFORE calling the original sample -> they are the raw logits.
+    np.savez_compressed(os.path.join(GOLD, "naive_b1.npz"), weight_seed=0, input_seed=1,
+                        phoneme_lens=[80], prompt_len=150, top_k=1, top_p=1.0, temperature=1.0,
+                        repetition_penalty=1.35, early_stop_num=40,
+                        logits=_pad_logits(hook.logits), y=y.numpy(), idx=idx)
+    print("naive_b1: idx", idx, "y", tuple(y.shape))
+
+
+def case_batch_b4(model):
+    L = [60, 80, 72, 80]
+    ids, lens, prompt, bert = synthetic.make_inputs(4, L, 150, seed=2)
+    y, idx, hook = _run(model, "infer_panel_batch_infer", (ids, lens, prompt, bert),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=24,
+                             repetition_penalty=1.35, max_len=80))
+    np.savez_compressed(os.path.join(GOLD, "batch_b4.npz"), weight_seed=0, input_seed=2,
+                        phoneme_lens=L, prompt_len=150, top_k=1, top_p=1.0, temperature=1.0,
+                        repetition_penalty=1.35, early_stop_num=24,
+                        logits=_pad_logits(hook.logits),
+                        y=np.stack([t.numpy() for t in y]), idx=np.array(idx))
+    print("batch_b4: idx", idx)
+
+
+def case_retire_b6():
+    sd = synthetic.make_state_dict(seed=3, eos_scale=1.4)
+    model = ref_harness.build_reference_model(sd, synthetic.S1V2_CONFIG)
+    L = [40, 64, 52, 33, 64, 47]
+    ids, lens, prompt, bert = synthetic.make_inputs(6, L, 60, seed=3)
+    y, idx, hook = _run(model, "infer_panel_batch_infer", (ids, lens, prompt, bert),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=30,
+                             repetition_penalty=1.35, max_len=64))
+    ymax = max(t.shape[0] for t in y)
+    ypad = np.full((6, ymax), -1, np.int64)
+    for i, t in enumerate(y):
+        ypad[i, : t.shape[0]] = t.numpy()
+    np.savez_compressed(os.path.join(GOLD, "retire_b6.npz"), weight_seed=3, eos_scale=1.4, input_seed=3,
+                        phoneme_lens=L, prompt_len=60, top_k=1, top_p=1.0, temperature=1.0,
+                        repetition_penalty=1.35, early_stop_num=30,
+                        logits=_pad_logits(hook.logits), y=ypad, idx=np.array(idx))
+    print("retire_b6: idx", idx)
+
+
+def case_reffree_b1(model):
+    ids, lens, _, bert = synthetic.make_inputs(1, [48], 0, seed=4)
+    y, idx, hook = _run(model, "infer_panel_naive", (ids[0][None], lens, None, bert[0][None]),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=20, repetition_penalty=1.35))
+    np.savez_compressed(os.path.join(GOLD, "reffree_b1.npz"), weight_seed=0, input_seed=4,
+                        phoneme_lens=[48], prompt_len=0, top_k=1, top_p=1.0, temperature=1.0,
+                        repetition_penalty=1.35, early_stop_num=20,
+                        logits=_pad_logits(hook.logits), y=y.numpy().astype(np.int64), idx=idx)
+    print("reffree_b1: idx", idx, "y", tuple(y.shape))
+
+
+def case_sampler_kat():
+    ref = ref_harness.import_reference()
+    from AR.models.utils import logits_to_probs  # reference function
+
+    rs = np.random.RandomState(7)
+    rows, prevs, params, probs_out, pen_out = [], [], [], [], []
+
+    def add(logits, prev, **kw):
+        lg = torch.tensor(logits, dtype=torch.float32)[None].clone()
+        pv = torch.tensor(prev, dtype=torch.int64)[None]
+        p = logits_to_probs(lg, pv, **kw)
+        rows.append(np.asarray(logits, np.float32))
+        prevs.append(np.asarray(prev, np.int64))
+        params.append([kw.get("temperature", 1.0), kw.get("top_k") or 0,
+                       kw.get("top_p") if kw.get("top_p") is not None else 100.0,
+                       kw.get("repetition_penalty", 1.0)])
+        probs_out.append(p[0].numpy())
+        pen_out.append(lg[0].numpy())  # penalised in place
+
+    base = rs.standard_normal(1025).astype(np.float32)
+    add(base, [3, 3, 7, 1000, 7], temperature=1.0, top_k=15, top_p=1.0, repetition_penalty=1.35)
+    add(base, [3, 5], temperature=0.7, top_k=5, top_p=0.8, repetition_penalty=1.35)
+    add(base[:1024], [0, 1023], temperature=1.0, top_k=1, top_p=1.0, repetition_penalty=1.35)
+    add(base, [], temperature=0.0, top_k=20, top_p=1.0, repetition_penalty=1.0)  # clamp to 1e-5
+    ties = base.copy()
+    ties[[10, 20, 30, 40]] = 5.0  # 4-way tie at the top, top_k=2 keeps all four (ties kept)
+    add(ties, [99], temperature=1.0, top_k=2, top_p=1.0, repetition_penalty=1.2)
+    # top-p boundary: softmax = [0.64, 0.24, 0.09, 0.03]-like; cum > top_p removed except the first
+    small = np.log(np.array([0.64, 0.24, 0.09, 0.03], np.float32))
+    add(small, [], temperature=1.0, top_k=4, top_p=0.7, repetition_penalty=1.0)
+    add(small, [], temperature=1.0, top_k=4, top_p=0.9, repetition_penalty=1.0)
+    add(small, [1], temperature=1.0, top_k=3, top_p=0.0, repetition_penalty=2.0)
+    neg = -np.abs(base)
+    add(neg, list(range(0, 1025, 3)), temperature=1.3, top_k=100, top_p=0.95, repetition_penalty=1.5)
+    add(base * 4, [1, 2, 3], temperature=1.0, top_k=2000, top_p=0.5, repetition_penalty=1.35)
+
+    n = len(rows)
+    width = np.array([r.shape[0] for r in rows])
+    lg = np.full((n, 1025), np.nan, np.float32)
+    pr = np.full((n, 1025), np.nan, np.float32)
+    pn = np.full((n, 1025), np.nan, np.float32)
+    pv = np.full((n, 400), -1, np.int64)
+    for i in range(n):
+        lg[i, : width[i]] = rows[i]
+        pr[i, : width[i]] = probs_out[i]
+        pn[i, : width[i]] = pen_out[i]
+        pv[i, : len(prevs[i])] = prevs[i]
+    np.savez_compressed(os.path.join(GOLD, "sampler_kat.npz"), logits=lg, width=width, prev=pv,
+                        params=np.array(params, np.float64), probs=pr, penalised=pn)
+    print("sampler_kat:", n, "rows")
+
+
+def main():
+    assert ref_harness.reference_available(), "run in the build container (needs /root/reference)"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    sd = synthetic.make_state_dict(seed=0)
+    model = ref_harness.build_reference_model(sd, synthetic.S1V2_CONFIG)
+    case_naive_b1(model)
+    case_batch_b4(model)
+    case_reffree_b1(model)
+    case_retire_b6()
+    case_sampler_kat()
+
+
+if __name__ == "__main__":
+    main()
