@@ -7,5 +7,17 @@ behind the C-ABI library ``libt2s_b200.so`` (include/t2s_b200.h); there is no CP
 engine without the library or without a CUDA device raises.
 """
 from . import synthetic  # noqa: F401
+from .decoder import (  # noqa: F401
+    engine_for,
+    infer_panel,
+    infer_panel_batch_infer,
+    infer_panel_naive,
+    infer_panel_naive_batched,
+    patch_reference,
+    unpatch_reference,
+)
+from .engine import EOS_WINDOW_BATCH, EOS_WINDOW_NAIVE, MAX_STEPS, InferResult, T2SEngine  # noqa: F401
 
-__all__ = ["synthetic"]
+__all__ = ["synthetic", "T2SEngine", "InferResult", "patch_reference", "unpatch_reference", "engine_for",
+           "infer_panel", "infer_panel_naive", "infer_panel_naive_batched", "infer_panel_batch_infer",
+           "MAX_STEPS", "EOS_WINDOW_NAIVE", "EOS_WINDOW_BATCH"]

@@ -1,0 +1,185 @@
+// common.cuh — constants, the device context, and small device helpers shared by every kernel.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace t2s {
+
+// ---- architecture constants of the s1 family (GPT_SoVITS/configs/s1longer-v2.yaml:19-31) -------
+constexpr int D = 512;          // hidden_dim
+constexpr int NH = 16;          // heads
+constexpr int DH = 32;          // head_dim
+constexpr int FF = 2048;        // 4*hidden (t2s_model.py:304)
+constexpr int V = 1025;         // vocab incl. EOS
+constexpr int VT = 65;          // 16-row feature tiles of the head (1040 rows, zero padded)
+constexpr int VPAD = VT * 16;
+constexpr int BERT = 1024;
+constexpr int PAGE = 64;        // KV positions per page
+constexpr int MAX_B = 256;      // max utterances per call
+constexpr int NT = 256;         // threads per CTA in every phase kernel
+constexpr int NW = NT / 32;
+constexpr int RT = 32;          // rows per projection tile (4 n-tiles of the m16n8k16 MMA)
+constexpr int XS = D + 8;       // bf16 row stride of the staged activation tile (bank-conflict free)
+constexpr int SEEN_WORDS = 33;  // ceil(1025/32)
+constexpr float LN_EPS = 1e-5f; // transformer.py:194
+// q is pre-scaled by log2(e)/sqrt(head_dim) so softmax uses exp2
+constexpr float QSCALE = 1.4426950408889634f * 0.17677669529663687f;
+
+// packed per-layer matrix arena (bf16 elements) and vector arena (fp32 elements)
+constexpr size_t OFF_WQKV = 0;
+constexpr size_t OFF_WO = OFF_WQKV + (size_t)3 * D * D;
+constexpr size_t OFF_W1 = OFF_WO + (size_t)D * D;
+constexpr size_t OFF_W2 = OFF_W1 + (size_t)FF * D;
+constexpr size_t LW = OFF_W2 + (size_t)D * FF;  // 3,145,728
+constexpr int VO_BQKV = 0, VO_BO = 1536, VO_B1 = 2048, VO_B2 = 4096, VO_G1 = 4608, VO_BE1 = 5120,
+              VO_G2 = 5632, VO_BE2 = 6144, LV = 6656;
+
+constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
+
+typedef __nv_bfloat16 bf16;
+
+// Everything a kernel needs, passed by value (fits the 4 KB parameter space).
+struct Ctx {
+  // model
+  const bf16* wmat;       // [n_layer][LW], each matrix in MMA-fragment tile order (see pack.cuh)
+  const float* wvec;      // [n_layer][LV]
+  const bf16* whead;      // ar_predict_layer, packed, VT tiles
+  const bf16* wbert;      // bert_proj.weight packed (32 tiles x 64 k-blocks)
+  const float* bbert;     // bert_proj.bias
+  const bf16* emb_audio;  // [V][D] row-major bf16
+  const bf16* emb_text;   // [phoneme_vocab][D]
+  const float* pe;        // [pe_len][D]
+  float alpha_audio, alpha_text;
+  int n_layer;
+  int pe_len;
+  // KV cache: pools [n_layer][n_pages][PAGE][D] bf16, page table [B][max_pages]
+  bf16* kpool;
+  bf16* vpool;
+  size_t kv_layer_stride;
+  const int* page_table;
+  int max_pages;
+  // rows of the current pass (prefill: every prompt position; decode: one per active sequence)
+  int* n_rows;
+  int* row_slot;
+  int* row_pos;
+  const int* head_rows;  // prefill: last row of each slot; NULL in decode (identity)
+  int x0_by_slot;        // layer-0 input indexed by slot (decode) or by row (prefill)
+  // activations
+  float* x0;
+  float* q;
+  bf16* attn;
+  float* y1;
+  bf16* h;
+  float* y2;
+  float2* stat2;
+  float* logits;  // [MAX_B][VPAD]
+  // decode attention split-KV scratch
+  float* part;
+  int* seg_cnt;
+  // session (indexed by slot = original batch index)
+  int B0, P, max_steps, eos_window, early_stop, top_k;
+  float top_p, temperature, rep_pen;
+  uint32_t seed_lo, seed_hi;
+  int* step;
+  int* seq_len;
+  int* active;
+  int* n_active;
+  int* done;
+  int* out_idx;
+  int* gen;      // [B0][max_steps]
+  int* sampled;  // [B0][max_steps]
+  int* greedy_rec;  // optional [B0][max_steps]: argmax of the penalised logits (test hook)
+  const int* forced;
+  int n_forced;
+  float* logits_rec;
+  int n_logits_rec;
+  uint32_t* seen;  // [B0][SEEN_WORDS]
+  // persistent-kernel grid barrier + watchdog, statistics
+  unsigned* bar;
+  int* abort_flag;
+  unsigned long long* stats;  // [0] kv positions, [1] steps, [2] sequence-steps
+};
+
+// ---- loads / stores ------------------------------------------------------------------------------
+// Weights are immutable for the kernel's lifetime: read-only path, do not pollute L1.
+__device__ __forceinline__ uint4 ld_weight16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+// Data produced by other CTAs inside the same (persistent) kernel: L2-coherent loads that bypass L1.
+__device__ __forceinline__ uint4 ld_cg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_cg_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_cg_i(const int* p) { return __ldcg(p); }
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// ---- grid barrier for the persistent kernel ---------------------------------------------------------
+// Monotonic arrival counter (zeroed by the host before launch).  Thread 0 of every CTA arrives with
+// release semantics and spins with acquire loads; a watchdog turns a lost CTA into an error instead
+// of a hung GPU.
+struct GridBarrier {
+  unsigned* counter;
+  int* abort_flag;
+  unsigned target;
+  unsigned ncta;
+  __device__ __forceinline__ void init(unsigned* c, int* a, unsigned n) {
+    counter = c; abort_flag = a; target = 0; ncta = n;
+  }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += ncta;
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+      unsigned v;
+      unsigned spins = 0;
+      long long t0 = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        if ((++spins & 0x3FFu) == 0) {
+          long long now = clock64();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 4000000000ll || __ldcg(abort_flag) != 0) {  // ~2 s at 1.9 GHz
+            atomicExch(abort_flag, 1);
+            break;
+          }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
+}  // namespace t2s

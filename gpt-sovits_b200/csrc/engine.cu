@@ -1,0 +1,720 @@
+// engine.cu — host side of libt2s_b200.so: the C ABI of include/t2s_b200.h.
+// Owns the packed weights, the paged KV pool and the session state; launches the kernels of
+// kernels.cuh.  No torch, no CPU compute path: everything numerical happens in the CUDA kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/t2s_b200.h"
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+
+using namespace t2s;
+
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct t2s_engine {
+  t2s_model_config cfg{};
+  int device = 0, num_sms = 0;
+  // weights
+  DevBuf wmat, wvec, whead, wbert, bbert, emb_audio, emb_text, pe, wrow;  // wrow: row-major bf16 copies for the TMA GEMM
+  float alpha_audio = 1.f, alpha_text = 1.f;
+  std::vector<char> loaded;  // per (tensor, layer)
+  // kv pool
+  DevBuf kpool, vpool;
+  size_t pool_pages = 0;
+  // session buffers
+  DevBuf ints, ints2, x0_rows, x0_slots, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
+  DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx;
+  Ctx cp{}, cd{};  // prefill / decode contexts
+  bool session = false;
+  int B = 0, P = 0, T = 0, n_text = 0, max_steps = 0;
+  const long long* prompt_dev = nullptr;
+  long long prompt_stride = 0;
+  std::vector<int> h_text_len, h_s0;
+  int n_qtiles = 0;
+  // device int layout inside `ints`
+  int *d_row_slot = nullptr, *d_row_pos = nullptr, *d_head_rows = nullptr, *d_text_off = nullptr, *d_text_len = nullptr,
+      *d_s0 = nullptr, *d_trow_slot = nullptr, *d_trow_j = nullptr, *d_trow_row = nullptr, *d_page_table = nullptr;
+  QTile* d_qtiles = nullptr;
+  // hooks / options
+  const int* forced = nullptr;
+  int n_forced = 0;
+  float* logits_rec = nullptr;
+  int n_logits_rec = 0;
+  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
+  // graph cache (decode_mode 0)
+  cudaGraphExec_t graph_exec = nullptr;
+  Ctx graph_ctx{};
+  int nodes_per_step = 0;
+  // stats
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  t2s_stats st{};
+  long long launches = 0;
+  int* h_pinned = nullptr;  // [4] pinned: n_active, step, abort
+};
+
+static size_t dtype_size(int dt) { return dt == T2S_F32 ? 4 : 2; }
+
+extern "C" const char* t2s_last_error(void) { return g_err.c_str(); }
+
+extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
+  if (!cfg || !out) return fail("t2s_create: null argument");
+  if (cfg->d_model != D || cfg->n_head != NH || cfg->d_ff != FF || cfg->vocab != V || cfg->bert_dim != BERT ||
+      cfg->eos != V - 1)
+    return fail("t2s_create: this build is specialised for d_model=512, n_head=16, d_ff=2048, vocab=1025, "
+                "bert_dim=1024, eos=1024 (got %d/%d/%d/%d/%d/%d)",
+                cfg->d_model, cfg->n_head, cfg->d_ff, cfg->vocab, cfg->bert_dim, cfg->eos);
+  if (cfg->n_layer < 1 || cfg->n_layer > 64) return fail("t2s_create: n_layer out of range");
+  if (cfg->max_batch < 1 || cfg->max_batch > MAX_B) return fail("t2s_create: max_batch must be in [1,%d]", MAX_B);
+  if (cfg->pe_len < 16) return fail("t2s_create: pe_len too small");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("t2s_create: no CUDA device; this library has no CPU fallback");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail("t2s_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major,
+                prop.minor);
+  t2s_engine* e = new t2s_engine();
+  e->cfg = *cfg;
+  e->device = dev;
+  e->num_sms = prop.multiProcessorCount;
+  const int L = cfg->n_layer;
+  int rc = 0;
+  rc |= e->wmat.ensure((size_t)L * LW * 2);
+  rc |= e->wvec.ensure((size_t)L * LV * 4);
+  rc |= e->whead.ensure((size_t)VPAD * D * 2);
+  rc |= e->wbert.ensure((size_t)D * BERT * 2);
+  rc |= e->bbert.ensure(D * 4);
+  rc |= e->emb_audio.ensure((size_t)V * D * 2);
+  rc |= e->emb_text.ensure((size_t)cfg->phoneme_vocab * D * 2);
+  rc |= e->pe.ensure((size_t)cfg->pe_len * D * 4);
+  rc |= e->wrow.ensure(((size_t)L * LW + (size_t)D * BERT) * 2);
+  rc |= e->logits.ensure((size_t)MAX_B * VPAD * 4);
+  rc |= e->part.ensure((size_t)(MAX_B + 1024) * PART_STRIDE * 4);
+  rc |= e->seg_cnt.ensure(MAX_B * 4);
+  rc |= e->misc.ensure(256);
+  rc |= e->x0_slots.ensure((size_t)MAX_B * D * 4);
+  rc |= e->seen.ensure((size_t)MAX_B * SEEN_WORDS * 4);
+  if (rc) { t2s_destroy(e); return 1; }
+  cudaMemset(e->seg_cnt.p, 0, MAX_B * 4);
+  cudaMemset(e->misc.p, 0, 256);
+  e->loaded.assign((size_t)T2S_W_COUNT * (L + 1), 0);
+  if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+      cudaMallocHost(&e->h_pinned, 64) != cudaSuccess) {
+    t2s_destroy(e);
+    return fail("t2s_create: event / pinned allocation failed");
+  }
+  // opt in to > 48 KB dynamic shared memory for the projection / persistent kernels
+  cudaFuncSetAttribute(k_phase<PH_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_OPROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_FFN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_FFN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_ATTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_phase<PH_PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_bert_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  cudaFuncSetAttribute(k_decode_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+  gemm_tc_init();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    t2s_destroy(e);
+    return fail("t2s_create: kernel attribute setup failed: %s", cudaGetErrorString(err));
+  }
+  e->st.num_sms = e->num_sms;
+  e->st.weight_bytes_per_step = ((int64_t)L * LW + (int64_t)V * D) * 2 + (int64_t)L * LV * 4;
+  e->st.kv_bytes_per_position = (int64_t)L * 2 * D * 2;
+  *out = e;
+  return 0;
+}
+
+extern "C" void t2s_destroy(t2s_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
+                    &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
+                    &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
+                    &e->bert_rows, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
+  for (DevBuf* b : bufs) b->release();
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  delete e;
+}
+
+// ---- weights ---------------------------------------------------------------------------------------------
+extern "C" int t2s_load_tensor(t2s_engine* e, int32_t id, int32_t layer, const void* data, int32_t dtype,
+                               int64_t numel, int32_t on_device, void* stream_) {
+  if (!e || !data) return fail("t2s_load_tensor: null argument");
+  if (id < 0 || id >= T2S_W_COUNT) return fail("t2s_load_tensor: bad tensor id %d", id);
+  if (dtype < 0 || dtype > 2) return fail("t2s_load_tensor: bad dtype %d", dtype);
+  cudaStream_t s = (cudaStream_t)stream_;
+  const bool per_layer = id >= T2S_W_IN_PROJ_W;
+  if (per_layer && (layer < 0 || layer >= e->cfg.n_layer)) return fail("t2s_load_tensor: layer %d out of range", layer);
+  struct Spec { int64_t n; int rows, cols; };
+  const int PV = e->cfg.phoneme_vocab;
+  Spec sp;
+  switch (id) {
+    case T2S_W_BERT_PROJ_W: sp = {(int64_t)D * BERT, D, BERT}; break;
+    case T2S_W_BERT_PROJ_B: sp = {D, 0, 0}; break;
+    case T2S_W_TEXT_EMB: sp = {(int64_t)PV * D, PV, D}; break;
+    case T2S_W_TEXT_ALPHA: case T2S_W_AUDIO_ALPHA: sp = {1, 0, 0}; break;
+    case T2S_W_AUDIO_EMB: sp = {(int64_t)V * D, V, D}; break;
+    case T2S_W_PE: sp = {(int64_t)e->cfg.pe_len * D, 0, 0}; break;
+    case T2S_W_PREDICT: sp = {(int64_t)V * D, V, D}; break;
+    case T2S_W_IN_PROJ_W: sp = {(int64_t)3 * D * D, 3 * D, D}; break;
+    case T2S_W_IN_PROJ_B: sp = {3 * D, 0, 0}; break;
+    case T2S_W_OUT_PROJ_W: sp = {(int64_t)D * D, D, D}; break;
+    case T2S_W_LIN1_W: sp = {(int64_t)FF * D, FF, D}; break;
+    case T2S_W_LIN1_B: sp = {FF, 0, 0}; break;
+    case T2S_W_LIN2_W: sp = {(int64_t)D * FF, D, FF}; break;
+    default: sp = {D, 0, 0}; break;  // out_proj bias, lin2 bias, norms
+  }
+  if (numel != sp.n) return fail("t2s_load_tensor: tensor %d expects %lld elements, got %lld", id, (long long)sp.n, (long long)numel);
+  // stage on device
+  const void* src = data;
+  DevBuf tmp;
+  if (!on_device) {
+    if (tmp.ensure((size_t)numel * dtype_size(dtype))) return 1;
+    CK(cudaMemcpyAsync(tmp.p, data, (size_t)numel * dtype_size(dtype), cudaMemcpyHostToDevice, s));
+    src = tmp.p;
+  }
+  const int blocks = 592, threads = 256;
+  auto pack = [&](bf16* dst, int N, int K, int tiles) {
+    k_pack_matrix<<<blocks, threads, 0, s>>>(dst, src, dtype, N, K, tiles);
+    e->launches++;
+  };
+  auto cvt_f32 = [&](float* dst, size_t n) {
+    k_convert_f32<<<blocks, threads, 0, s>>>(dst, src, dtype, n);
+    e->launches++;
+  };
+  auto cvt_b16 = [&](bf16* dst, size_t n) {
+    k_convert_bf16<<<blocks, threads, 0, s>>>(dst, src, dtype, n);
+    e->launches++;
+  };
+  bf16* wl = e->wmat.as<bf16>() + (size_t)layer * LW;
+  bf16* wr = e->wrow.as<bf16>() + (size_t)layer * LW;  // row-major copies (TMA GEMM operand B)
+  float* vl = e->wvec.as<float>() + (size_t)layer * LV;
+  switch (id) {
+    case T2S_W_BERT_PROJ_W:
+      pack(e->wbert.as<bf16>(), D, BERT, D / 16);
+      cvt_b16(e->wrow.as<bf16>() + (size_t)e->cfg.n_layer * LW, (size_t)D * BERT);
+      break;
+    case T2S_W_BERT_PROJ_B: cvt_f32(e->bbert.as<float>(), D); break;
+    case T2S_W_TEXT_EMB: cvt_b16(e->emb_text.as<bf16>(), (size_t)PV * D); break;
+    case T2S_W_AUDIO_EMB: cvt_b16(e->emb_audio.as<bf16>(), (size_t)V * D); break;
+    case T2S_W_TEXT_ALPHA: case T2S_W_AUDIO_ALPHA: {
+      cvt_f32(e->misc.as<float>() + 32, 1);
+      float v = 0.f;
+      CK(cudaMemcpyAsync(&v, e->misc.as<float>() + 32, 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      (id == T2S_W_TEXT_ALPHA ? e->alpha_text : e->alpha_audio) = v;
+      break;
+    }
+    case T2S_W_PE: cvt_f32(e->pe.as<float>(), (size_t)e->cfg.pe_len * D); break;
+    case T2S_W_PREDICT: pack(e->whead.as<bf16>(), V, D, VT); break;
+    case T2S_W_IN_PROJ_W: pack(wl + OFF_WQKV, 3 * D, D, 3 * D / 16); cvt_b16(wr + OFF_WQKV, (size_t)3 * D * D); break;
+    case T2S_W_OUT_PROJ_W: pack(wl + OFF_WO, D, D, D / 16); cvt_b16(wr + OFF_WO, (size_t)D * D); break;
+    case T2S_W_LIN1_W: pack(wl + OFF_W1, FF, D, FF / 16); cvt_b16(wr + OFF_W1, (size_t)FF * D); break;
+    case T2S_W_LIN2_W: pack(wl + OFF_W2, D, FF, D / 16); cvt_b16(wr + OFF_W2, (size_t)D * FF); break;
+    case T2S_W_IN_PROJ_B: cvt_f32(vl + VO_BQKV, 3 * D); break;
+    case T2S_W_OUT_PROJ_B: cvt_f32(vl + VO_BO, D); break;
+    case T2S_W_LIN1_B: cvt_f32(vl + VO_B1, FF); break;
+    case T2S_W_LIN2_B: cvt_f32(vl + VO_B2, D); break;
+    case T2S_W_NORM1_W: cvt_f32(vl + VO_G1, D); break;
+    case T2S_W_NORM1_B: cvt_f32(vl + VO_BE1, D); break;
+    case T2S_W_NORM2_W: cvt_f32(vl + VO_G2, D); break;
+    case T2S_W_NORM2_B: cvt_f32(vl + VO_BE2, D); break;
+    default: break;
+  }
+  CK(cudaGetLastError());
+  if (!on_device) { CK(cudaStreamSynchronize(s)); tmp.release(); }
+  e->loaded[(size_t)id * (e->cfg.n_layer + 1) + (per_layer ? layer : 0)] = 1;
+  return 0;
+}
+
+static int check_loaded(t2s_engine* e) {
+  const int L = e->cfg.n_layer;
+  for (int id = 0; id < T2S_W_COUNT; ++id) {
+    const bool per_layer = id >= T2S_W_IN_PROJ_W;
+    for (int l = 0; l < (per_layer ? L : 1); ++l)
+      if (!e->loaded[(size_t)id * (L + 1) + l]) return fail("weights incomplete: tensor id %d layer %d was never loaded", id, l);
+  }
+  return 0;
+}
+
+// ---- options / hooks ----------------------------------------------------------------------------------
+extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
+  if (!e) return fail("t2s_set_option: null engine");
+  switch (opt) {
+    case T2S_OPT_DECODE_MODE: if (v != 0 && v != 1) return fail("decode mode must be 0 or 1"); e->decode_mode = (int)v; break;
+    case T2S_OPT_PREFILL_GEMM: if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1"); e->prefill_gemm = (int)v; break;
+    case T2S_OPT_NUM_CTAS: if (v < 0 || v > 1024) return fail("num_ctas out of range"); e->num_ctas = (int)v; break;
+    case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
+    default: return fail("unknown option %d", opt);
+  }
+  return 0;
+}
+extern "C" int t2s_set_forced_tokens(t2s_engine* e, const int32_t* forced, int32_t n) {
+  if (!e) return fail("null engine");
+  e->forced = forced; e->n_forced = forced ? n : 0;
+  return 0;
+}
+extern "C" int t2s_set_logits_capture(t2s_engine* e, float* buf, int32_t n) {
+  if (!e) return fail("null engine");
+  e->logits_rec = buf; e->n_logits_rec = buf ? n : 0;
+  return 0;
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------------
+template <int PH>
+static void launch_phase(t2s_engine* e, const Ctx& c, int layer, int grid, cudaStream_t s) {
+  k_phase<PH><<<grid, NT, SMEM_MAX, s>>>(c, layer);
+  e->launches++;
+}
+
+static void launch_decode_step(t2s_engine* e, const Ctx& c, cudaStream_t s) {
+  const int g = e->num_sms;
+  for (int l = 0; l < c.n_layer; ++l) {
+    launch_phase<PH_QKV>(e, c, l, g, s);
+    launch_phase<PH_ATTN>(e, c, l, g, s);
+    launch_phase<PH_OPROJ>(e, c, l, g, s);
+    launch_phase<PH_FFN1>(e, c, l, g, s);
+    launch_phase<PH_FFN2>(e, c, l, g, s);
+  }
+  launch_phase<PH_HEAD>(e, c, 0, g, s);
+  launch_phase<PH_SAMPLE>(e, c, 0, std::min(std::max(c.B0, 1), g), s);
+  launch_phase<PH_PLAN>(e, c, 0, 1, s);
+}
+
+// ---- prefill ---------------------------------------------------------------------------------------------
+extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) {
+  if (!e || !rq) return fail("t2s_prefill: null argument");
+  if (check_loaded(e)) return 1;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int B = rq->batch, P = rq->prompt_len;
+  if (B < 1 || B > e->cfg.max_batch) return fail("t2s_prefill: batch %d outside [1,%d]", B, e->cfg.max_batch);
+  if (P < 0) return fail("t2s_prefill: negative prompt_len");
+  if (P > 0 && !rq->prompt) return fail("t2s_prefill: prompt_len > 0 but prompt is NULL");
+  if (rq->top_k < 1) return fail("t2s_prefill: top_k must be >= 1 (the reference's torch.topk fails otherwise)");
+  if (rq->max_steps < 1) return fail("t2s_prefill: max_steps must be >= 1");
+  if (!(rq->repetition_penalty > 0.f)) return fail("t2s_prefill: repetition_penalty must be > 0");
+  if (rq->bert_dtype < 0 || rq->bert_dtype > 2) return fail("t2s_prefill: bad bert_dtype");
+  if (!rq->phoneme_ids || !rq->phoneme_lens || !rq->bert || !rq->bert_stride_c || !rq->bert_stride_t)
+    return fail("t2s_prefill: null input pointer");
+  int steps_cap = rq->max_steps;
+  if (rq->early_stop_num >= 0) steps_cap = std::min(steps_cap, rq->early_stop_num + 1);
+  std::vector<int> text_len(B), text_off(B), s0(B), row0(B);
+  int n_text = 0, T = 0, max_pages = 0;
+  for (int b = 0; b < B; ++b) {
+    const int L = rq->phoneme_lens[b];
+    if (L < 1) return fail("t2s_prefill: utterance %d has %d phonemes", b, L);
+    text_len[b] = L; text_off[b] = n_text; n_text += L;
+    s0[b] = L + P; row0[b] = T; T += L + P;
+    if (std::max(L, P + steps_cap) >= e->cfg.pe_len)
+      return fail("t2s_prefill: position %d exceeds the %d-entry positional table (embedding.py:52)", std::max(L, P + steps_cap), e->cfg.pe_len);
+    max_pages = std::max(max_pages, (s0[b] + steps_cap + PAGE - 1) / PAGE);
+  }
+  // ---- KV pool + page table (pages handed out contiguously per slot)
+  std::vector<int> page_table((size_t)B * max_pages, 0);
+  size_t pages = 0;
+  for (int b = 0; b < B; ++b) {
+    const int np = (s0[b] + steps_cap + PAGE - 1) / PAGE;
+    for (int i = 0; i < np; ++i) page_table[(size_t)b * max_pages + i] = (int)pages++;
+  }
+  if (pages > e->pool_pages) {
+    const size_t bytes = (size_t)e->cfg.n_layer * pages * PAGE * D * 2;
+    CK(cudaStreamSynchronize(s));
+    if (e->kpool.ensure(bytes) || e->vpool.ensure(bytes)) return 1;
+    e->pool_pages = pages;
+  }
+  // ---- host-built index arrays
+  std::vector<int> row_slot(T), row_pos(T), head_rows(B), trow_slot(n_text), trow_j(n_text), trow_row(n_text);
+  std::vector<QTile> qtiles;
+  for (int b = 0, r = 0, tr = 0; b < B; ++b) {
+    for (int j = 0; j < s0[b]; ++j, ++r) {
+      row_slot[r] = b; row_pos[r] = j;
+      if (j < text_len[b]) { trow_slot[tr] = b; trow_j[tr] = j; trow_row[tr] = r; ++tr; }
+    }
+    head_rows[b] = r - 1;
+    for (int q0 = 0; q0 < s0[b]; q0 += 64) qtiles.push_back(QTile{b, q0, row0[b] + q0, std::min(64, s0[b] - q0)});
+  }
+  const size_t R = (size_t)std::max(T, MAX_B);
+  const size_t n_ints = (size_t)2 * R + B * 4 + (size_t)3 * n_text + page_table.size() + qtiles.size() * 4 + 64;
+  int rc = 0;
+  rc |= e->ints.ensure(n_ints * 4);
+  rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
+  rc |= e->x0_rows.ensure((size_t)T * D * 4);
+  rc |= e->q.ensure(R * D * 4);
+  rc |= e->attn.ensure(R * D * 2);
+  rc |= e->y1.ensure(R * D * 4);
+  rc |= e->h.ensure(R * FF * 2);
+  rc |= e->y2.ensure(R * D * 4);
+  rc |= e->stat2.ensure(R * 8);
+  rc |= e->gen.ensure((size_t)B * rq->max_steps * 4);
+  rc |= e->sampled.ensure((size_t)B * rq->max_steps * 4);
+  rc |= e->bert_rows.ensure((size_t)n_text * BERT * 2);
+  if (rc) return 1;
+  // pack the int arrays into one upload
+  std::vector<int> hi(n_ints, 0);
+  size_t o = 0;
+  auto put = [&](const int* src, size_t n) { size_t at = o; if (n) memcpy(&hi[o], src, n * 4); o += n; return at; };
+  const size_t o_row_slot = put(row_slot.data(), T); o = R;
+  const size_t o_row_pos = put(row_pos.data(), T); o = 2 * R;
+  const size_t o_head = put(head_rows.data(), B);
+  const size_t o_toff = put(text_off.data(), B);
+  const size_t o_tlen = put(text_len.data(), B);
+  const size_t o_s0 = put(s0.data(), B);
+  const size_t o_ts = put(trow_slot.data(), n_text);
+  const size_t o_tj = put(trow_j.data(), n_text);
+  const size_t o_tr = put(trow_row.data(), n_text);
+  const size_t o_pt = put(page_table.data(), page_table.size());
+  o = (o + 3) & ~(size_t)3;
+  const size_t o_qt = put(reinterpret_cast<const int*>(qtiles.data()), qtiles.size() * 4);
+  CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
+  int* di = e->ints.as<int>();
+  e->d_row_slot = di + o_row_slot; e->d_row_pos = di + o_row_pos; e->d_head_rows = di + o_head;
+  e->d_text_off = di + o_toff; e->d_text_len = di + o_tlen; e->d_s0 = di + o_s0;
+  e->d_trow_slot = di + o_ts; e->d_trow_j = di + o_tj; e->d_trow_row = di + o_tr; e->d_page_table = di + o_pt;
+  e->d_qtiles = reinterpret_cast<QTile*>(di + o_qt);
+  e->n_qtiles = (int)qtiles.size();
+  // ---- inputs: device pointers, or host buffers copied here (end-to-end form)
+  const long long* d_ids = reinterpret_cast<const long long*>(rq->phoneme_ids);
+  const long long* d_prompt = reinterpret_cast<const long long*>(rq->prompt);
+  long long prompt_stride = rq->prompt_row_stride;
+  std::vector<const void*> bert_ptrs(B);
+  std::vector<long long> bsc(B), bst(B);
+  const size_t es = dtype_size(rq->bert_dtype);
+  if (rq->inputs_on_host) {
+    if (e->in_ids.ensure((size_t)n_text * 8) || e->in_bert.ensure((size_t)n_text * BERT * es) ||
+        e->in_prompt.ensure((size_t)std::max(1, B * P) * 8))
+      return 1;
+    CK(cudaMemcpyAsync(e->in_ids.p, rq->phoneme_ids, (size_t)n_text * 8, cudaMemcpyHostToDevice, s));
+    d_ids = e->in_ids.as<long long>();
+    if (P > 0) {
+      if (rq->prompt_row_stride == 0) {
+        CK(cudaMemcpyAsync(e->in_prompt.p, rq->prompt, (size_t)P * 8, cudaMemcpyHostToDevice, s));
+        prompt_stride = 0;
+      } else {
+        CK(cudaMemcpy2DAsync(e->in_prompt.p, (size_t)P * 8, rq->prompt, (size_t)rq->prompt_row_stride * 8, (size_t)P * 8, B,
+                             cudaMemcpyHostToDevice, s));
+        prompt_stride = P;
+      }
+      d_prompt = e->in_prompt.as<long long>();
+    }
+    for (int b = 0; b < B; ++b) {
+      if (rq->bert_stride_t[b] != 1 || rq->bert_stride_c[b] != text_len[b])
+        return fail("t2s_prefill: host BERT features must be contiguous [1024, L]");
+      char* dst = e->in_bert.as<char>() + (size_t)text_off[b] * BERT * es;
+      CK(cudaMemcpyAsync(dst, rq->bert[b], (size_t)text_len[b] * BERT * es, cudaMemcpyHostToDevice, s));
+      bert_ptrs[b] = dst; bsc[b] = text_len[b]; bst[b] = 1;
+    }
+  } else {
+    for (int b = 0; b < B; ++b) { bert_ptrs[b] = rq->bert[b]; bsc[b] = rq->bert_stride_c[b]; bst[b] = rq->bert_stride_t[b]; }
+  }
+  if (e->in_bert_ptrs.ensure((size_t)B * 24)) return 1;
+  CK(cudaMemcpyAsync(e->in_bert_ptrs.p, bert_ptrs.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->in_bert_ptrs.as<char>() + (size_t)B * 8, bsc.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->in_bert_ptrs.as<char>() + (size_t)B * 16, bst.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // host staging vectors go out of scope below; uploads are tiny
+  e->prompt_dev = d_prompt; e->prompt_stride = prompt_stride;
+  e->B = B; e->P = P; e->T = T; e->n_text = n_text; e->max_steps = rq->max_steps;
+  e->h_text_len = text_len; e->h_s0 = s0;
+  // ---- contexts
+  Ctx c{};
+  c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
+  c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
+  c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
+  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
+  c.kpool = e->kpool.as<bf16>(); c.vpool = e->vpool.as<bf16>();
+  c.kv_layer_stride = e->pool_pages * PAGE * D;
+  c.page_table = e->d_page_table; c.max_pages = max_pages;
+  int* i2 = e->ints2.as<int>();
+  c.n_rows = i2 + 0; c.n_active = i2 + 1; c.step = i2 + 2; c.abort_flag = i2 + 3;
+  c.bar = reinterpret_cast<unsigned*>(i2 + 4);
+  c.stats = reinterpret_cast<unsigned long long*>(i2 + 8);  // 3 x u64, 8-byte aligned
+  c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
+  c.row_slot = e->d_row_slot; c.row_pos = e->d_row_pos;
+  c.q = e->q.as<float>(); c.attn = e->attn.as<bf16>(); c.y1 = e->y1.as<float>(); c.h = e->h.as<bf16>();
+  c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>(); c.logits = e->logits.as<float>();
+  c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
+  c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
+  c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
+  c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
+  c.seed_lo = (uint32_t)(rq->seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(rq->seed >> 32);
+  c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
+  c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
+  c.seen = e->seen.as<uint32_t>();
+  e->cp = c; e->cp.x0 = e->x0_rows.as<float>(); e->cp.x0_by_slot = 0; e->cp.head_rows = e->d_head_rows;
+  e->cd = c; e->cd.x0 = e->x0_slots.as<float>(); e->cd.x0_by_slot = 1; e->cd.head_rows = nullptr;
+  const Ctx& cp = e->cp;
+  // ---- launch
+  CK(cudaEventRecord(e->ev0, s));
+  const int g = e->num_sms;
+  k_init_session<<<B, 128, 0, s>>>(e->cd, d_prompt, prompt_stride, e->d_s0);
+  CK(cudaMemcpyAsync(cp.n_rows, &e->T, 4, cudaMemcpyHostToDevice, s));
+  k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride);
+  const void* const* dptr = reinterpret_cast<const void* const*>(e->in_bert_ptrs.p);
+  const long long* dsc = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 8);
+  const long long* dst_ = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 16);
+  if (rq->bert_dtype == T2S_F32)
+    k_bert_rows<float><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
+  else if (rq->bert_dtype == T2S_F16)
+    k_bert_rows<__half><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
+  else
+    k_bert_rows<bf16><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
+  k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
+  e->launches += 4;
+  for (int l = 0; l < cp.n_layer; ++l) {
+    launch_phase<PH_QKV>(e, cp, l, g, s);
+    k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+    e->launches++;
+    launch_phase<PH_OPROJ>(e, cp, l, g, s);
+    launch_phase<PH_FFN1>(e, cp, l, g, s);
+    launch_phase<PH_FFN2>(e, cp, l, g, s);
+  }
+  launch_phase<PH_HEAD>(e, cp, 0, g, s);           // rows = n_active = B, gathered through head_rows
+  launch_phase<PH_SAMPLE>(e, e->cd, 0, std::min(B, g), s);  // step 0 sample; writes the decode-side x0
+  launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);
+  CK(cudaEventRecord(e->ev1, s));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->st.prefill_ms = ms;
+  e->st.prefill_rows = T;
+  e->session = true;
+  return 0;
+}
+
+// ---- decode ----------------------------------------------------------------------------------------------
+static int read_state(t2s_engine* e, cudaStream_t s, int* n_active, int* step, int* aborted) {
+  CK(cudaMemcpyAsync(e->h_pinned, e->cd.n_rows, 16, cudaMemcpyDeviceToHost, s));  // n_rows, n_active, step, abort
+  CK(cudaStreamSynchronize(s));
+  *n_active = e->h_pinned[1]; *step = e->h_pinned[2]; *aborted = e->h_pinned[3];
+  return 0;
+}
+
+extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, int32_t* steps_run) {
+  if (!e) return fail("t2s_decode: null engine");
+  if (!e->session) return fail("t2s_decode: no session (call t2s_prefill first)");
+  cudaStream_t s = (cudaStream_t)stream_;
+  int n_active = 0, step0 = 0, aborted = 0;
+  if (read_state(e, s, &n_active, &step0, &aborted)) return 1;
+  int budget = max_new_steps < 0 ? e->max_steps : max_new_steps;
+  unsigned long long stats0[3];
+  CK(cudaMemcpyAsync(stats0, e->cd.stats, 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(e->ev0, s));
+  if (n_active > 0 && budget > 0) {
+    if (e->decode_mode == 1) {
+      int grid = e->num_ctas > 0 ? e->num_ctas : e->num_sms;
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_persistent, NT, SMEM_MAX));
+      if (per_sm < 1) return fail("t2s_decode: persistent kernel does not fit on an SM");
+      grid = std::min(grid, per_sm * e->num_sms);
+      CK(cudaMemsetAsync(e->cd.bar, 0, 4, s));
+      Ctx c = e->cd;
+      int steps = budget;
+      void* args[] = {&c, &steps};
+      CK(cudaLaunchCooperativeKernel((const void*)k_decode_persistent, dim3(grid), dim3(NT), args, SMEM_MAX, s));
+      e->launches++;
+    } else {
+      // one graph = one decode step (122 kernel nodes); re-captured only when the context changes
+      if (!e->graph_exec || memcmp(&e->graph_ctx, &e->cd, sizeof(Ctx)) != 0) {
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        const long long before = e->launches;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        launch_decode_step(e, e->cd, cs);
+        cudaGraph_t graph;
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        e->nodes_per_step = (int)(e->launches - before);
+        e->launches = before;
+        if (ce != cudaSuccess) { cudaStreamDestroy(cs); return fail("graph capture failed: %s", cudaGetErrorString(ce)); }
+        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+        e->graph_ctx = e->cd;
+      }
+      int done_steps = 0;
+      while (done_steps < budget && n_active > 0) {
+        const int chunk = std::min(e->check_steps, budget - done_steps);
+        for (int i = 0; i < chunk; ++i) CK(cudaGraphLaunch(e->graph_exec, s));
+        e->launches += (long long)chunk * e->nodes_per_step;
+        done_steps += chunk;
+        CK(cudaMemcpyAsync(e->h_pinned, e->cd.n_rows, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        n_active = e->h_pinned[1];
+      }
+    }
+  }
+  CK(cudaEventRecord(e->ev1, s));
+  CK(cudaGetLastError());
+  int step1 = 0;
+  if (read_state(e, s, &n_active, &step1, &aborted)) return 1;
+  if (aborted) return fail("t2s_decode: grid barrier watchdog fired (a CTA never arrived); results are invalid");
+  unsigned long long stats1[3];
+  CK(cudaMemcpyAsync(stats1, e->cd.stats, 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  // plan() accounts a step when it schedules it; steps scheduled but not run (budget hit) are excluded
+  e->st.decode_ms = ms;
+  e->st.decode_steps = step1 - step0;
+  e->st.decode_kv_positions = (int64_t)(stats1[0] - stats0[0]);
+  e->st.decode_tokens = (int64_t)(stats1[2] - stats0[2]);
+  if (steps_run) *steps_run = step1 - step0;
+  return 0;
+}
+
+// ---- results ---------------------------------------------------------------------------------------------
+extern "C" int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride, int32_t tokens_on_host,
+                          int32_t* idx_out, void* stream_) {
+  if (!e || !tokens_out || !idx_out) return fail("t2s_result: null argument");
+  if (!e->session) return fail("t2s_result: no session");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int width = e->P + e->max_steps;
+  if (row_stride < width) return fail("t2s_result: row_stride %lld < P + max_steps = %d", (long long)row_stride, width);
+  if (e->out_idx.ensure((size_t)e->B * 4)) return 1;
+  long long* dst = reinterpret_cast<long long*>(tokens_out);
+  long long stride = row_stride;
+  if (tokens_on_host) {
+    if (e->out_tokens.ensure((size_t)e->B * width * 8)) return 1;
+    dst = e->out_tokens.as<long long>();
+    stride = width;
+  }
+  k_finalize<<<e->B, 256, 0, s>>>(e->cd, e->prompt_dev, e->prompt_stride, dst, stride, e->out_idx.as<int>());
+  e->launches++;
+  CK(cudaGetLastError());
+  if (tokens_on_host)
+    CK(cudaMemcpy2DAsync(tokens_out, (size_t)row_stride * 8, dst, (size_t)width * 8, (size_t)width * 8, e->B,
+                         cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(idx_out, e->out_idx.p, (size_t)e->B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int t2s_generate(t2s_engine* e, const t2s_request* rq, int64_t* tokens_out, int64_t row_stride,
+                            int32_t tokens_on_host, int32_t* idx_out, void* stream) {
+  if (t2s_prefill(e, rq, stream)) return 1;
+  int32_t n = 0;
+  if (t2s_decode(e, -1, stream, &n)) return 1;
+  return t2s_result(e, tokens_out, row_stride, tokens_on_host, idx_out, stream);
+}
+
+extern "C" int t2s_get_sampled(t2s_engine* e, int32_t* out, int32_t n_steps, void* stream_) {
+  if (!e || !out) return fail("t2s_get_sampled: null argument");
+  if (!e->session) return fail("t2s_get_sampled: no session");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int n = std::min(n_steps, e->max_steps);
+  CK(cudaMemcpy2DAsync(out, (size_t)n_steps * 4, e->sampled.p, (size_t)e->max_steps * 4, (size_t)n * 4, e->B,
+                       cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, int32_t width, const int32_t* prev,
+                                int32_t m, int32_t top_k, float top_p, float temperature, float repetition_penalty,
+                                uint64_t seed, int32_t step, int32_t* tok_out, int32_t* greedy_out, void* stream_) {
+  if (!e || !logits || !tok_out || !greedy_out) return fail("t2s_sampler_test: null argument");
+  if (n < 1 || n > MAX_B) return fail("t2s_sampler_test: n out of range");
+  if (width != V && width != V - 1) return fail("t2s_sampler_test: width must be 1024 or 1025");
+  if (top_k < 1 || step < 0) return fail("t2s_sampler_test: bad top_k / step");
+  cudaStream_t s = (cudaStream_t)stream_;
+  e->session = false;  // clobbers the session state
+  const int ms = step + 2;
+  if (e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4) || e->gen.ensure((size_t)n * ms * 4 * 3)) return 1;
+  std::vector<float> lg((size_t)n * VPAD, 0.f);
+  for (int r = 0; r < n; ++r) memcpy(&lg[(size_t)r * VPAD], logits + (size_t)r * V, V * 4);
+  std::vector<uint32_t> seen((size_t)n * SEEN_WORDS, 0u);
+  for (int r = 0; r < n; ++r)
+    for (int j = 0; j < m; ++j) {
+      const int t = prev ? prev[(size_t)r * m + j] : -1;
+      if (t >= 0 && t < V) seen[(size_t)r * SEEN_WORDS + (t >> 5)] |= 1u << (t & 31);
+    }
+  std::vector<int> i2(16 + 4 * MAX_B, 0);
+  i2[0] = n; i2[1] = n; i2[2] = step;
+  for (int r = 0; r < n; ++r) i2[16 + MAX_B + r] = r;  // active = identity
+  CK(cudaMemcpyAsync(e->logits.p, lg.data(), lg.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->seen.p, seen.data(), seen.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->ints2.p, i2.data(), i2.size() * 4, cudaMemcpyHostToDevice, s));
+  Ctx c{};
+  int* d2 = e->ints2.as<int>();
+  c.n_rows = d2; c.n_active = d2 + 1; c.step = d2 + 2; c.abort_flag = d2 + 3;
+  c.seq_len = d2 + 16; c.active = d2 + 16 + MAX_B; c.done = d2 + 16 + 2 * MAX_B; c.out_idx = d2 + 16 + 3 * MAX_B;
+  c.logits = e->logits.as<float>(); c.seen = e->seen.as<uint32_t>();
+  c.gen = e->gen.as<int>(); c.sampled = c.gen + (size_t)n * ms; c.greedy_rec = c.gen + (size_t)2 * n * ms;
+  c.B0 = n; c.P = 0; c.max_steps = ms; c.eos_window = (width == V) ? 0 : step + 1; c.early_stop = -1; c.top_k = top_k;
+  c.top_p = top_p; c.temperature = temperature; c.rep_pen = repetition_penalty;
+  c.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(seed >> 32);
+  c.emb_audio = e->emb_audio.as<bf16>(); c.pe = e->pe.as<float>(); c.pe_len = e->cfg.pe_len; c.alpha_audio = 0.f;
+  c.x0 = e->x0_slots.as<float>();
+  launch_phase<PH_SAMPLE>(e, c, 0, std::min(n, e->num_sms), s);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(tok_out, 4, c.sampled + step, (size_t)ms * 4, 4, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpy2DAsync(greedy_out, 4, c.greedy_rec + step, (size_t)ms * 4, 4, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int t2s_get_stats(t2s_engine* e, t2s_stats* out) {
+  if (!e || !out) return fail("t2s_get_stats: null argument");
+  e->st.kernel_launches = e->launches;
+  e->st.decode_mode = e->decode_mode;
+  *out = e->st;
+  return 0;
+}

@@ -1,0 +1,279 @@
+// kernels.cuh — __global__ entry points: per-phase wrappers (graph mode), the persistent cooperative
+// decode kernel, prefill-only kernels (input embedding, prefix-LM attention) and weight packing.
+#pragma once
+#include "phases.cuh"
+
+namespace t2s {
+
+constexpr size_t SMEM_PROJ = sizeof(ProjSmem);
+constexpr size_t SMEM_ATTN = sizeof(AttnSmem);
+constexpr size_t SMEM_SAMP = sizeof(SampSmem);
+constexpr size_t SMEM_MAX = SMEM_PROJ > SMEM_ATTN ? (SMEM_PROJ > SMEM_SAMP ? SMEM_PROJ : SMEM_SAMP)
+                                                  : (SMEM_ATTN > SMEM_SAMP ? SMEM_ATTN : SMEM_SAMP);
+
+// ---- one kernel per phase (graph mode and prefill) ---------------------------------------------------
+enum { PH_QKV = 0, PH_ATTN, PH_OPROJ, PH_FFN1, PH_FFN2, PH_HEAD, PH_SAMPLE, PH_PLAN };
+
+template <int PH>
+__global__ void __launch_bounds__(NT, 1) k_phase(Ctx c, int layer) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  if (PH == PH_QKV) {
+    phase_qkv(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+  } else if (PH == PH_ATTN) {
+    phase_attn_decode(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<AttnSmem*>(smem));
+  } else if (PH == PH_OPROJ) {
+    phase_oproj(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+  } else if (PH == PH_FFN1) {
+    phase_ffn1(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+  } else if (PH == PH_FFN2) {
+    phase_ffn2(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+  } else if (PH == PH_HEAD) {
+    phase_head(c, ld_cg_i(c.n_active), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+  } else if (PH == PH_SAMPLE) {
+    phase_sample(c, ld_cg_i(c.n_active), cta, ncta, *reinterpret_cast<SampSmem*>(smem));
+  } else if (PH == PH_PLAN) {
+    if (cta == 0) phase_plan(c, reinterpret_cast<int*>(smem));
+  }
+}
+
+// ---- persistent cooperative decode: every remaining step of the request in ONE launch ----------------
+// Grid = one CTA per SM (cooperative launch guarantees co-residency).  Phases are separated by the
+// GridBarrier; the loop exits when the active list is empty (all CTAs read the same count after a
+// barrier) or after max_new_steps.
+__global__ void __launch_bounds__(NT, 1) k_decode_persistent(Ctx c, int max_new_steps) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  GridBarrier bar;
+  bar.init(c.bar, c.abort_flag, (unsigned)ncta);
+  ProjSmem& ps = *reinterpret_cast<ProjSmem*>(smem);
+  AttnSmem& as = *reinterpret_cast<AttnSmem*>(smem);
+  SampSmem& ss = *reinterpret_cast<SampSmem*>(smem);
+  for (int it = 0; it < max_new_steps; ++it) {
+    const int n = ld_cg_i(c.n_active);
+    if (n == 0 || __ldcg(c.abort_flag) != 0) break;
+    for (int layer = 0; layer < c.n_layer; ++layer) {
+      phase_qkv(c, layer, n, cta, ncta, ps);
+      bar.sync();
+      phase_attn_decode(c, layer, n, cta, ncta, as);
+      bar.sync();
+      phase_oproj(c, layer, n, cta, ncta, ps);
+      bar.sync();
+      phase_ffn1(c, layer, n, cta, ncta, ps);
+      bar.sync();
+      phase_ffn2(c, layer, n, cta, ncta, ps);
+      bar.sync();
+    }
+    phase_head(c, n, cta, ncta, ps);
+    bar.sync();
+    phase_sample(c, n, cta, ncta, ss);
+    bar.sync();
+    if (cta == 0) phase_plan(c, reinterpret_cast<int*>(smem));
+    bar.sync();
+  }
+}
+
+// ---- session initialisation ----------------------------------------------------------------------------
+// One CTA per slot: seen-bitmap from the prompt (previous_tokens = y includes the prompt,
+// t2s_model.py:714), counters, identity active list.
+__global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_row_stride, const int* s0) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ unsigned bits[SEEN_WORDS];
+  if (tid < SEEN_WORDS) bits[tid] = 0u;
+  __syncthreads();
+  for (int i = tid; i < c.P; i += blockDim.x) {
+    const long long t = prompt[(long long)b * prompt_row_stride + i];
+    if (t >= 0 && t < V) atomicOr(&bits[t >> 5], 1u << (t & 31));
+  }
+  __syncthreads();
+  if (tid < SEEN_WORDS) c.seen[(size_t)b * SEEN_WORDS + tid] = bits[tid];
+  if (tid == 0) {
+    c.done[b] = 0;
+    c.out_idx[b] = -1;
+    c.seq_len[b] = s0[b];
+    c.active[b] = b;
+    c.seg_cnt[b] = 0;
+    if (b == 0) {
+      *c.n_active = c.B0;
+      *c.step = 0;
+      *c.abort_flag = 0;
+      c.stats[0] = c.stats[1] = c.stats[2] = 0ull;
+    }
+  }
+}
+
+// ---- prefill input embedding (t2s_model.py:611-622, 636-641; embedding.py:74-78) ----------------------
+// Row r = (slot, j).  Text rows:  emb_text[ph] + bert_proj.bias + alpha_t*pe[j]   (+ bert_proj GEMM, added
+// afterwards by the OUT_BERT projection phase);  audio rows: emb_audio[tok] + alpha_a*pe[j - L].
+__global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, const int* text_off,
+                             const int* text_len, const long long* prompt, long long prompt_row_stride) {
+  const int r = blockIdx.x;
+  if (r >= n_rows) return;
+  const int slot = c.row_slot[r], j = c.row_pos[r], L = text_len[slot];
+  float* out = c.x0 + (size_t)r * D;
+  if (j < L) {
+    const long long ph = phoneme_ids[text_off[slot] + j];
+    const bf16* er = c.emb_text + (size_t)ph * D;
+    const float* pr = c.pe + (size_t)j * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+      out[d] = __bfloat162float(er[d]) + c.bbert[d] + c.alpha_text * pr[d];
+  } else {
+    const long long tok = prompt[(long long)slot * prompt_row_stride + (j - L)];
+    const bf16* er = c.emb_audio + (size_t)tok * D;
+    const float* pr = c.pe + (size_t)(j - L) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = __bfloat162float(er[d]) + c.alpha_audio * pr[d];
+  }
+}
+
+// BERT features arrive feature-major per utterance ([1024, L_i], TTS.py:1215); gather them token-major
+// in bf16 for the bert_proj GEMM.  One CTA per text row.
+template <typename T>
+__global__ void k_bert_rows(bf16* out, const void* const* bert, const long long* stride_c,
+                            const long long* stride_t, const int* trow_slot, const int* trow_j) {
+  const int r = blockIdx.x;
+  const int slot = trow_slot[r], j = trow_j[r];
+  const T* src = reinterpret_cast<const T*>(bert[slot]);
+  const long long sc = stride_c[slot], st = stride_t[slot];
+  for (int ch = threadIdx.x; ch < BERT; ch += blockDim.x)
+    out[(size_t)r * BERT + ch] = __float2bfloat16_rn((float)src[ch * sc + j * st]);
+}
+
+__global__ void __launch_bounds__(NT, 1) k_bert_proj(Ctx c, const bf16* bert_rows, const int* trow_row, int n_text_rows) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ProjArgs a{};
+  a.w = c.wbert; a.n_tiles = D / 16; a.k_slices = BERT / 512;
+  a.in_b16 = bert_rows; a.in_stride = BERT; a.out_idx = trow_row;
+  proj_phase<IN_BF16, OUT_BERT>(c, a, n_text_rows, blockIdx.x, gridDim.x, *reinterpret_cast<ProjSmem*>(smem));
+}
+
+// ---- prefill attention with the prefix-LM mask (t2s_model.py:644-683 + SDPA :157) ------------------------
+// Row j of a sequence with L text positions sees keys [0, L) if j < L (text: bidirectional over text,
+// no audio) and [0, j] otherwise (audio: all text + causal audio).  Left padding never materialises.
+// CTA = (64-query tile of one sequence, head); one thread per query, K/V tiles staged in shared memory
+// as fp32 and read by broadcast.  Reads the bf16 K/V just written to the cache pages, so prefill and
+// decode see identical (rounded) keys and values.
+struct QTile { int slot, q0, row0, n_q; };  // row0 = global row index of query q0
+
+__global__ void __launch_bounds__(64) k_prefill_attn(Ctx c, int layer, const QTile* tiles, const int* text_len) {
+  const QTile qt = tiles[blockIdx.x];
+  const int head = blockIdx.y, tid = threadIdx.x;
+  const int L = text_len[qt.slot];
+  __shared__ float Ks[64][DH];
+  __shared__ float Vs[64][DH];
+  const bool has_q = tid < qt.n_q;
+  const int j = qt.q0 + tid;
+  const int nvis = has_q ? ((j < L) ? L : j + 1) : 0;
+  const int last = qt.q0 + qt.n_q - 1;
+  const int kv_end = (qt.q0 < L) ? max(L, last + 1) : last + 1;
+  float q[DH], acc[DH], m = -INFINITY, l = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) { q[d] = 0.f; acc[d] = 0.f; }
+  if (has_q) {
+    const float* qr = c.q + (size_t)(qt.row0 + tid) * D + head * DH;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(qr + d);
+      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+    }
+  }
+  const bf16* kbase = c.kpool + (size_t)layer * c.kv_layer_stride;
+  const bf16* vbase = c.vpool + (size_t)layer * c.kv_layer_stride;
+  const int* pt = c.page_table + qt.slot * c.max_pages;
+  for (int kt = 0; kt < kv_end; kt += 64) {
+    __syncthreads();
+    {
+      const int p = kt + tid;
+      if (p < kv_end) {
+        const size_t off = ((size_t)pt[p >> 6] * PAGE + (p & (PAGE - 1))) * D + head * DH;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 kk = *reinterpret_cast<const uint4*>(kbase + off + ch * 8);
+          const uint4 vv = *reinterpret_cast<const uint4*>(vbase + off + ch * 8);
+          float* kd = &Ks[tid][ch * 8];
+          float* vd = &Vs[tid][ch * 8];
+          kd[0] = bf_lo(kk.x); kd[1] = bf_hi(kk.x); kd[2] = bf_lo(kk.y); kd[3] = bf_hi(kk.y);
+          kd[4] = bf_lo(kk.z); kd[5] = bf_hi(kk.z); kd[6] = bf_lo(kk.w); kd[7] = bf_hi(kk.w);
+          vd[0] = bf_lo(vv.x); vd[1] = bf_hi(vv.x); vd[2] = bf_lo(vv.y); vd[3] = bf_hi(vv.y);
+          vd[4] = bf_lo(vv.z); vd[5] = bf_hi(vv.z); vd[6] = bf_lo(vv.w); vd[7] = bf_hi(vv.w);
+        }
+      }
+    }
+    __syncthreads();
+    const int jmax = min(64, nvis - kt);
+    for (int jj = 0; jj < jmax; ++jj) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&Ks[jj][d]);
+        s += q[d] * kk.x + q[d + 1] * kk.y + q[d + 2] * kk.z + q[d + 3] * kk.w;
+      }
+      if (s > m) {
+        const float corr = exp2f(m - s);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] *= corr;
+        m = s;
+      }
+      const float p = exp2f(s - m);
+      l += p;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&Vs[jj][d]);
+        acc[d] += p * vv.x; acc[d + 1] += p * vv.y; acc[d + 2] += p * vv.z; acc[d + 3] += p * vv.w;
+      }
+    }
+  }
+  if (has_q) {
+    const float inv = 1.0f / l;
+    bf16* o = c.attn + (size_t)(qt.row0 + tid) * D + head * DH;
+#pragma unroll
+    for (int d = 0; d < DH; d += 2)
+      *reinterpret_cast<uint32_t*>(o + d) = pack_bf2(acc[d] * inv, acc[d + 1] * inv);
+  }
+}
+
+// ---- results: prompt ++ kept tokens, original batch order (t2s_model.py:733,753,779) -----------------
+__global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_stride, long long* out,
+                           long long row_stride, int* idx_out) {
+  const int b = blockIdx.x;
+  const int idx = c.out_idx[b];
+  const int n = idx < 0 ? 0 : idx;
+  long long* o = out + (long long)b * row_stride;
+  for (int i = threadIdx.x; i < c.P; i += blockDim.x) o[i] = prompt[(long long)b * prompt_row_stride + i];
+  for (int i = threadIdx.x; i < c.max_steps; i += blockDim.x)
+    o[c.P + i] = (i < n) ? (long long)c.gen[(size_t)b * c.max_steps + i] : -1ll;
+  if (threadIdx.x == 0) idx_out[b] = idx;
+}
+
+// ---- weight packing -----------------------------------------------------------------------------------
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, size_t i) {
+  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const bf16*>(p)[i]);
+}
+// src [N][K] row-major -> dst in m16n8k16 A-fragment order: ((tile*KB + kb)*32 + lane)*8 + j where
+// lane = g*4+t holds (row g | g+8, col 2t+{0,1} | +8): j = 0,1:(g,2t) 2,3:(g+8,2t) 4,5:(g,2t+8) 6,7:(g+8,2t+8)
+__global__ void k_pack_matrix(bf16* dst, const void* src, int dtype, int N, int K, int n_tiles) {
+  const size_t total = (size_t)n_tiles * 16 * K;
+  const int KB = K / 16;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int j = o & 7, lane = (o >> 3) & 31;
+    const size_t blk = o >> 8;
+    const int kb = blk % KB, tile = blk / KB;
+    const int g = lane >> 2, t = lane & 3;
+    const int row = tile * 16 + g + ((j & 2) ? 8 : 0);
+    const int col = kb * 16 + 2 * t + (j & 1) + ((j & 4) ? 8 : 0);
+    const float v = (row < N) ? load_as_float(src, dtype, (size_t)row * K + col) : 0.f;
+    dst[o] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void k_convert_bf16(bf16* dst, const void* src, int dtype, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(load_as_float(src, dtype, i));
+}
+__global__ void k_convert_f32(float* dst, const void* src, int dtype, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = load_as_float(src, dtype, i);
+}
+
+}  // namespace t2s

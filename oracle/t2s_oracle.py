@@ -177,6 +177,8 @@ class T2SOracle:
         """Returns dict(tokens=[per-slot int64 arrays prompt+kept], idx=[...], logits=[steps][n,1025]
         (raw, before penalty; rows in active order), active=[steps] slot lists, sampled=[B,steps],
         margins=[B,steps])."""
+        import time
+        t_start = time.perf_counter()
         B = len(phoneme_ids)
         P = 0 if prompt is None else int(prompt.shape[1])
         noise_fn = noise_fn or (lambda slot, step, n: so.exp_noise(seed, slot, step, n))
@@ -197,6 +199,7 @@ class T2SOracle:
         lens = np.array(S0, dtype=np.int64)
         out = dict(logits=[], active=[], sampled=np.full((B, max_steps), -1, np.int64),
                    margins=np.ones((B, max_steps), np.float32))
+        out["t_prefill"] = time.perf_counter() - t_start
         for step in range(max_steps):
             logits = (hid[active] @ self.wp.T).astype(np.float32)  # [n, 1025]
             if record_logits:
@@ -230,6 +233,7 @@ class T2SOracle:
             sel = np.array(active)
             hid[sel] = self.decode_step(x, K, V, sel, lens[sel])
             lens[sel] += 1
+        out["t_total"] = time.perf_counter() - t_start
         out["tokens"] = [np.array(hist[b] + gen[b][: idx_out[b]], dtype=np.int64) for b in range(B)]
         out["idx"] = [int(i) for i in idx_out]
         out["generated"] = gen
