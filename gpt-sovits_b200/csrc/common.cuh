@@ -66,6 +66,7 @@ struct Ctx {
   int* row_pos;
   const int* head_rows;  // prefill: last row of each slot; NULL in decode (identity)
   int x0_by_slot;        // layer-0 input indexed by slot (decode) or by row (prefill)
+  int deterministic;     // 1: no floating-point atomics anywhere (FFN2 K-slices summed inside one unit)
   // activations
   float* x0;
   float* q;

@@ -88,7 +88,7 @@ struct t2s_engine {
   int n_forced = 0;
   float* logits_rec = nullptr;
   int n_logits_rec = 0;
-  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
+  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16, deterministic = 1;
   // graph cache (decode_mode 0)
   cudaGraphExec_t graph_exec = nullptr;
   Ctx graph_ctx{};
@@ -301,6 +301,7 @@ extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
     case T2S_OPT_DECODE_MODE: if (v != 0 && v != 1) return fail("decode mode must be 0 or 1"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM: if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1"); e->prefill_gemm = (int)v; break;
     case T2S_OPT_NUM_CTAS: if (v < 0 || v > 1024) return fail("num_ctas out of range"); e->num_ctas = (int)v; break;
+    case T2S_OPT_DETERMINISTIC: if (v != 0 && v != 1) return fail("deterministic must be 0 or 1"); e->deterministic = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
   }
@@ -476,7 +477,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
   c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
   c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
-  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
+  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len; c.deterministic = e->deterministic;
   c.kpool = e->kpool.as<bf16>(); c.vpool = e->vpool.as<bf16>();
   c.kv_layer_stride = e->pool_pages * PAGE * D;
   c.page_table = e->d_page_table; c.max_pages = max_pages;
@@ -533,6 +534,10 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->st.prefill_ms = ms;
+  e->st.decode_ms = 0.0;
+  e->st.decode_steps = 0;
+  e->st.decode_kv_positions = 0;
+  e->st.decode_tokens = 0;
   e->st.prefill_rows = T;
   e->session = true;
   return 0;
@@ -553,9 +558,6 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   int n_active = 0, step0 = 0, aborted = 0;
   if (read_state(e, s, &n_active, &step0, &aborted)) return 1;
   int budget = max_new_steps < 0 ? e->max_steps : max_new_steps;
-  unsigned long long stats0[3];
-  CK(cudaMemcpyAsync(stats0, e->cd.stats, 24, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(e->ev0, s));
   if (n_active > 0 && budget > 0) {
     if (e->decode_mode == 1) {
@@ -612,11 +614,12 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   CK(cudaStreamSynchronize(s));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-  // plan() accounts a step when it schedules it; steps scheduled but not run (budget hit) are excluded
-  e->st.decode_ms = ms;
-  e->st.decode_steps = step1 - step0;
-  e->st.decode_kv_positions = (int64_t)(stats1[0] - stats0[0]);
-  e->st.decode_tokens = (int64_t)(stats1[2] - stats0[2]);
+  // Session-cumulative: plan() accounts a decode step (its attended KV positions and active sequences)
+  // when it schedules it, starting with the plan that follows the prefill's step-0 sample.
+  e->st.decode_ms += ms;
+  e->st.decode_steps = step1 - 1;
+  e->st.decode_kv_positions = (int64_t)stats1[0];
+  e->st.decode_tokens = (int64_t)stats1[2];
   if (steps_run) *steps_run = step1 - step0;
   return 0;
 }

@@ -141,7 +141,7 @@ __global__ void k_bert_rows(bf16* out, const void* const* bert, const long long*
 __global__ void __launch_bounds__(NT, 1) k_bert_proj(Ctx c, const bf16* bert_rows, const int* trow_row, int n_text_rows) {
   extern __shared__ __align__(16) unsigned char smem[];
   ProjArgs a{};
-  a.w = c.wbert; a.n_tiles = D / 16; a.k_slices = BERT / 512;
+  a.w = c.wbert; a.n_tiles = D / 16; a.k_slices = BERT / 512; a.k_seq = BERT / 512;
   a.in_b16 = bert_rows; a.in_stride = BERT; a.out_idx = trow_row;
   proj_phase<IN_BF16, OUT_BERT>(c, a, n_text_rows, blockIdx.x, gridDim.x, *reinterpret_cast<ProjSmem*>(smem));
 }

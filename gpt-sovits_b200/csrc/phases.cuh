@@ -31,6 +31,7 @@ struct ProjArgs {
   const bf16* w;       // packed weights of this matrix
   int n_tiles;         // 16-feature tiles
   int k_slices;        // 512-wide K slices per feature row
+  int k_seq;           // slices accumulated sequentially inside one unit (k_slices/k_seq units run in parallel)
   const float* in_f32; // IN_X0 / IN_LN source rows [.,D]
   const bf16* in_b16;  // IN_BF16 source rows
   int in_stride;       // IN_BF16 row stride (elements)
@@ -137,11 +138,15 @@ __device__ __forceinline__ void proj_epilogue(const Ctx& c, const ProjArgs& a, i
   } else if (OUT == OUT_FFN1) {
     c.h[(size_t)r * FF + f] = __float2bfloat16_rn(fmaxf(acc + a.bias[f], 0.f));
   } else if (OUT == OUT_FFN2) {
-    atomicAdd(c.y2 + (size_t)r * D + f, acc);
+    float* p = c.y2 + (size_t)r * D + f;
+    if (a.k_seq == a.k_slices) *p = __ldcg(p) + acc;  // single writer: deterministic
+    else atomicAdd(p, acc);                           // split-K across CTAs
   } else if (OUT == OUT_HEAD) {
     if (f < V) c.logits[(size_t)r * VPAD + f] = acc;
   } else if (OUT == OUT_BERT) {
-    atomicAdd(c.x0 + (size_t)a.out_idx[r] * D + f, acc);
+    float* p = c.x0 + (size_t)a.out_idx[r] * D + f;
+    if (a.k_seq == a.k_slices) *p = __ldcg(p) + acc;
+    else atomicAdd(p, acc);
   }
 }
 
@@ -149,7 +154,7 @@ template <int IN, int OUT>
 __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta, int ncta, ProjSmem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int n_units = a.n_tiles * a.k_slices;
+  const int n_units = a.n_tiles * (a.k_slices / a.k_seq);
   const int kb_per_row = a.k_slices * 32;
   float lg[16], lb[16];
   if (IN == IN_LN) {
@@ -165,16 +170,8 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
     for (int j = 0; j < 16; ++j) { lg[j] = 1.f; lb[j] = 0.f; }
   }
   for (int u = cta; u < n_units; u += ncta) {
-    const int nt = u % a.n_tiles, ks = u / a.n_tiles;
-    // this warp's 4 A fragments (k-blocks ks*32 + warp*4 .. +3 of feature tile nt)
-    uint4 af[4];
-    const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * kb_per_row + ks * 32 + warp * 4) * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = ld_weight16(wp + i * 32);
+    const int nt = u % a.n_tiles, kp = u / a.n_tiles;
     for (int r0 = 0; r0 < n_rows; r0 += RT) {
-      __syncthreads();  // previous tile's readers of xs / red are done
-      proj_stage<IN, OUT>(c, a, sm, r0, n_rows, nt, ks, lg, lb);
-      __syncthreads();
       const int rows_here = min(RT, n_rows - r0);
       const int n8 = (rows_here + 7) >> 3;
       float acc[4][4];
@@ -182,14 +179,25 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int kq = 0; kq < a.k_seq; ++kq) {
+        const int ks = kp * a.k_seq + kq;
+        // this warp's 4 A fragments (k-blocks ks*32 + warp*4 .. +3 of feature tile nt)
+        uint4 af[4];
+        const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * kb_per_row + ks * 32 + warp * 4) * 32 + lane;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k0 = (warp * 4 + i) * 16;
+        for (int i = 0; i < 4; ++i) af[i] = ld_weight16(wp + i * 32);
+        __syncthreads();  // previous readers of xs / red are done
+        proj_stage<IN, OUT>(c, a, sm, r0, n_rows, nt, ks, lg, lb);
+        __syncthreads();
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          if (n < n8) {
-            const uint32_t* xr = reinterpret_cast<const uint32_t*>(sm.xs + (n * 8 + g) * XS + k0);
-            mma_bf16_16816(acc[n], af[i], xr[t], xr[4 + t]);
+        for (int i = 0; i < 4; ++i) {
+          const int k0 = (warp * 4 + i) * 16;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (n < n8) {
+              const uint32_t* xr = reinterpret_cast<const uint32_t*>(sm.xs + (n * 8 + g) * XS + k0);
+              mma_bf16_16816(acc[n], af[i], xr[t], xr[4 + t]);
+            }
           }
         }
       }
@@ -219,7 +227,7 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
 __device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WQKV;
-  a.n_tiles = 3 * D / 16; a.k_slices = 1; a.layer = layer;
+  a.n_tiles = 3 * D / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
   a.bias = c.wvec + (size_t)layer * LV + VO_BQKV;
   if (layer == 0) {
     a.in_f32 = c.x0; a.in_idx = c.x0_by_slot ? c.row_slot : nullptr;
@@ -234,7 +242,7 @@ __device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, i
 __device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WO;
-  a.n_tiles = D / 16; a.k_slices = 1; a.layer = layer;
+  a.n_tiles = D / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
   a.in_b16 = c.attn; a.in_stride = D;
   a.bias = c.wvec + (size_t)layer * LV + VO_BO;
   if (layer > 0) {
@@ -246,7 +254,7 @@ __device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows,
 __device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W1;
-  a.n_tiles = FF / 16; a.k_slices = 1; a.layer = layer;
+  a.n_tiles = FF / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
   a.in_f32 = c.y1;
   a.ln_g = c.wvec + (size_t)layer * LV + VO_G1;
   a.ln_b = c.wvec + (size_t)layer * LV + VO_BE1;
@@ -257,14 +265,14 @@ __device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, 
 __device__ __forceinline__ void phase_ffn2(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W2;
-  a.n_tiles = D / 16; a.k_slices = FF / 512; a.layer = layer;
+  a.n_tiles = D / 16; a.k_slices = FF / 512; a.k_seq = c.deterministic ? FF / 512 : 1; a.layer = layer;
   a.in_b16 = c.h; a.in_stride = FF;
   proj_phase<IN_BF16, OUT_FFN2>(c, a, n_rows, cta, ncta, sm);
 }
 __device__ __forceinline__ void phase_head(const Ctx& c, int n_rows, int cta, int ncta, ProjSmem& sm) {
   ProjArgs a{};
   a.w = c.whead;
-  a.n_tiles = VT; a.k_slices = 1; a.layer = c.n_layer;
+  a.n_tiles = VT; a.k_slices = 1; a.k_seq = 1; a.layer = c.n_layer;
   a.in_f32 = c.y2; a.in_idx = c.head_rows;
   a.ln_g = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_G2;
   a.ln_b = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_BE2;

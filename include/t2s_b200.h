@@ -143,14 +143,16 @@ enum {
   T2S_OPT_DECODE_MODE = 0,   /* 0: one kernel per phase, CUDA-graph replay; 1: persistent cooperative kernel */
   T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */
   T2S_OPT_NUM_CTAS = 2,      /* persistent grid size (0 = one CTA per SM) */
-  T2S_OPT_CHECK_STEPS = 3    /* graph mode: host checks the active count every this many steps */
+  T2S_OPT_CHECK_STEPS = 3,   /* graph mode: host checks the active count every this many steps */
+  T2S_OPT_DETERMINISTIC = 4  /* 1 (default): no floating-point atomics, results reproducible bit for bit;
+                                0: FFN2 split-K partials are combined with fp32 atomics (4x more units) */
 };
 int t2s_set_option(t2s_engine* e, int32_t option, int64_t value);
 
 typedef struct {
   double prefill_ms;          /* device time of the last t2s_prefill (CUDA events on `stream`) */
-  double decode_ms;           /* device time of the last t2s_decode */
-  int64_t decode_steps;       /* decode steps executed in the last t2s_decode */
+  double decode_ms;           /* device time of t2s_decode, cumulative over the current session */
+  int64_t decode_steps;       /* decode steps (after the prefill step) executed in the session */
   int64_t decode_tokens;      /* sequence-steps (sum of active sequences over those steps) */
   int64_t decode_kv_positions;/* sum over those sequence-steps of attended KV positions */
   int64_t kernel_launches;    /* kernels this library launched since t2s_create */

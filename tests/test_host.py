@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol that
+include/t2s_b200.h declares (no compute calls without a GPU), error behaviour without a device, the
+synthetic generator, and the multi-GPU utterance sharding over gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpt_sovits_b200 import _lib, shard, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "t2s_b200.h")).read()
+    declared = set(re.findall(r"\b(t2s_[a-z_]+)\s*\(", header))
+    declared -= {"t2s_engine"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    _lib.build()  # no-op when up to date; nvcc cross-compiles without a GPU
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side compiles to (x86-64 SysV): guards the ctypes mirror against drift
+    assert C.sizeof(_lib.ModelConfig) == 40
+    assert C.sizeof(_lib.Request) == 120
+    assert C.sizeof(_lib.Stats) == 80
+    assert _lib.Request.prompt_row_stride.offset == 64 and _lib.Request.seed.offset == 104
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_device_no_fallback():
+    import gpt_sovits_b200 as gsb
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gsb.T2SEngine(synthetic.S1V2_CONFIG)
+    lib = _lib.load()
+    cfg = _lib.ModelConfig(n_layer=24, d_model=512, n_head=16, d_ff=2048, vocab=1025, phoneme_vocab=732,
+                           bert_dim=1024, eos=1024, pe_len=4000, max_batch=32)
+    h = C.c_void_p()
+    assert lib.t2s_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CUDA device" in lib.t2s_last_error() or b"CUDA" in lib.t2s_last_error()
+    bad = _lib.ModelConfig(n_layer=24, d_model=1024, n_head=16, d_ff=4096, vocab=1025, phoneme_vocab=732,
+                           bert_dim=1024, eos=1024, pe_len=4000, max_batch=32)
+    assert lib.t2s_create(C.byref(bad), C.byref(h)) != 0
+    assert b"specialised" in lib.t2s_last_error()
+
+
+def test_synthetic_is_deterministic_and_bf16_exact():
+    a = synthetic.make_state_dict(seed=0, config={"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=2)})
+    b = synthetic.make_state_dict(seed=0, config={"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=2)})
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k])
+        assert torch.equal(a[k], a[k].bfloat16().float()), k  # bf16-representable
+    assert a["h.layers.1.self_attn.in_proj_weight"].shape == (1536, 512)
+    # pins the generator stream the goldens were made with
+    assert abs(float(a["ar_predict_layer.weight"].double().abs().sum()) - 18545.0) < 200.0
+    ids, lens, prompt, bert = synthetic.make_inputs(3, [5, 9, 7], 11, seed=1)
+    assert [t.shape[0] for t in ids] == [5, 9, 7] and prompt.shape == (3, 11) and prompt.stride(0) == 0
+    assert bert[1].shape == (1024, 9)
+    assert synthetic.config_lens(4, 60, 120, seed=2) == synthetic.config_lens(4, 60, 120, seed=2)
+
+
+def test_partition_is_balanced_and_complete():
+    costs = [120, 60, 61, 119, 90, 90, 75, 100, 64]
+    for world in (1, 2, 4, 8):
+        parts = shard.partition_utterances(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        if world <= 4:
+            assert max(loads) - min(loads) <= max(costs)
+    assert shard.partition_utterances([], 2) == [[], []]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, costs, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def fake_infer(indices):  # stands in for infer_panel_batch_infer on this rank's GPU
+        calls.append(list(indices))
+        ys = [torch.arange(3 + i, dtype=torch.int64) * (i + 1) for i in indices]
+        return ys, [i % 5 + 1 for i in indices]
+
+    y_list, idx_list = shard.sharded_infer(fake_infer, costs)
+    out_q.put((rank, calls, [y.tolist() for y in y_list], idx_list))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_infer_gloo_world2():
+    """N>1 path on CPU: two ranks, disjoint utterance shares, results identical on both ranks and in the
+    original order; the only communication is the final gather."""
+    costs = [80, 60, 120, 61, 95, 70, 110]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, costs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    results.sort()
+    (r0, c0, y0, i0), (r1, c1, y1, i1) = results
+    assert y0 == y1 and i0 == i1
+    assert len(c0) == 1 and len(c1) == 1 and sorted(c0[0] + c1[0]) == list(range(7)) and not set(c0[0]) & set(c1[0])
+    for i in range(7):
+        assert y0[i] == (np.arange(3 + i) * (i + 1)).tolist() and i0[i] == i % 5 + 1
