@@ -20,11 +20,11 @@ F32, F16, BF16 = 0, 1, 2
  W_IN_PROJ_W, W_IN_PROJ_B, W_OUT_PROJ_W, W_OUT_PROJ_B, W_LIN1_W, W_LIN1_B, W_LIN2_W, W_LIN2_B,
  W_NORM1_W, W_NORM1_B, W_NORM2_W, W_NORM2_B, W_COUNT) = range(21)
 
-OPT_DECODE_MODE, OPT_PREFILL_GEMM, OPT_NUM_CTAS, OPT_CHECK_STEPS, OPT_DETERMINISTIC = 0, 1, 2, 3, 4
+OPT_DECODE_MODE, OPT_PREFILL_GEMM, OPT_NUM_CTAS, OPT_CHECK_STEPS = 0, 1, 2, 3
 
 EXPORTS = ["t2s_create", "t2s_destroy", "t2s_last_error", "t2s_load_tensor", "t2s_prefill", "t2s_decode",
            "t2s_result", "t2s_generate", "t2s_set_forced_tokens", "t2s_set_logits_capture",
-           "t2s_get_sampled", "t2s_set_option", "t2s_get_stats", "t2s_sampler_test"]
+           "t2s_get_sampled", "t2s_set_option", "t2s_get_stats", "t2s_sampler_test", "t2s_bench_barrier", "t2s_set_timeline"]
 
 
 class ModelConfig(C.Structure):
@@ -114,6 +114,8 @@ def load() -> C.CDLL:
     lib.t2s_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.t2s_sampler_test.argtypes = [vp, vp, i32, i32, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_uint64, i32,
                                      vp, vp, vp]
+    lib.t2s_bench_barrier.argtypes = [vp, i32, i32, C.POINTER(C.c_float), vp]
+    lib.t2s_set_timeline.argtypes = [vp, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("t2s_destroy", "t2s_last_error"):
             getattr(lib, name).restype = i32

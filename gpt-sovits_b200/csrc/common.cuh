@@ -64,9 +64,9 @@ struct Ctx {
   int* n_rows;
   int* row_slot;
   int* row_pos;
+  long long* row_kvoff;   // element offset of the row's KV position inside one layer's pool
   const int* head_rows;  // prefill: last row of each slot; NULL in decode (identity)
   int x0_by_slot;        // layer-0 input indexed by slot (decode) or by row (prefill)
-  int deterministic;     // 1: no floating-point atomics anywhere (FFN2 K-slices summed inside one unit)
   // activations
   float* x0;
   float* q;
@@ -79,6 +79,8 @@ struct Ctx {
   // decode attention split-KV scratch
   float* part;
   int* seg_cnt;
+  int* attn_desc;   // [attn_ctas][2] int4 {row, pbeg, pend, (j << 16) | count}, written by phase_plan
+  int attn_ctas;    // grid size of the decode attention phase (fixed for the session)
   // session (indexed by slot = original batch index)
   int B0, P, max_steps, eos_window, early_stop, top_k;
   float top_p, temperature, rep_pen;
@@ -101,6 +103,9 @@ struct Ctx {
   unsigned* bar;
   int* abort_flag;
   unsigned long long* stats;  // [0] kv positions, [1] steps, [2] sequence-steps
+  long long* timeline;        // measurement hook: [ncta][tl_slots][2] (arrive, release) SM clocks of one step
+  int tl_step, tl_slots;
+  long long* probe;           // measurement hook: [ncta][2][32] intra-phase marks (qkv, attention of layer 1)
 };
 
 // ---- loads / stores ------------------------------------------------------------------------------
@@ -153,20 +158,23 @@ struct GridBarrier {
   int* abort_flag;
   unsigned target;
   unsigned ncta;
+  long long* tl;  // timeline row of this CTA (or nullptr)
+  int tl_k, tl_n;
   __device__ __forceinline__ void init(unsigned* c, int* a, unsigned n) {
-    counter = c; abort_flag = a; target = 0; ncta = n;
+    counter = c; abort_flag = a; target = 0; ncta = n; tl = nullptr; tl_k = 0; tl_n = 0;
   }
   __device__ __forceinline__ void sync() {
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (tl && tl_k < tl_n) tl[2 * tl_k] = clock64();
       target += ncta;
-      __threadfence();
+      // release: cumulative over the CTA's writes ordered before it by the bar.sync above
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
       unsigned v;
       unsigned spins = 0;
       long long t0 = 0;
       for (;;) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         if (v >= target) break;
         if ((++spins & 0x3FFu) == 0) {
           long long now = clock64();
@@ -177,7 +185,8 @@ struct GridBarrier {
           }
         }
       }
-      __threadfence();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire side of the relaxed poll
+      if (tl && tl_k < tl_n) { tl[2 * tl_k + 1] = clock64(); ++tl_k; }
     }
     __syncthreads();
   }

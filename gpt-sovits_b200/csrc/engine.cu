@@ -70,7 +70,7 @@ struct t2s_engine {
   DevBuf kpool, vpool;
   size_t pool_pages = 0;
   // session buffers
-  DevBuf ints, ints2, x0_rows, x0_slots, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
+  DevBuf ints, ints2, kvoff, attn_desc, x0_rows, x0_slots, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
   DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx;
   Ctx cp{}, cd{};  // prefill / decode contexts
   bool session = false;
@@ -88,7 +88,10 @@ struct t2s_engine {
   int n_forced = 0;
   float* logits_rec = nullptr;
   int n_logits_rec = 0;
-  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16, deterministic = 1;
+  long long* timeline = nullptr;
+  long long* probe = nullptr;
+  int tl_step = 0, tl_slots = 0;
+  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
   // graph cache (decode_mode 0)
   cudaGraphExec_t graph_exec = nullptr;
   Ctx graph_ctx{};
@@ -142,6 +145,7 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   rc |= e->logits.ensure((size_t)MAX_B * VPAD * 4);
   rc |= e->part.ensure((size_t)(MAX_B + 1024) * PART_STRIDE * 4);
   rc |= e->seg_cnt.ensure(MAX_B * 4);
+  rc |= e->attn_desc.ensure((size_t)1024 * 2 * 16);
   rc |= e->misc.ensure(256);
   rc |= e->x0_slots.ensure((size_t)MAX_B * D * 4);
   rc |= e->seen.ensure((size_t)MAX_B * SEEN_WORDS * 4);
@@ -182,7 +186,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
-                    &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
+                    &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
   for (DevBuf* b : bufs) b->release();
@@ -298,10 +302,9 @@ static int check_loaded(t2s_engine* e) {
 extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
-    case T2S_OPT_DECODE_MODE: if (v != 0 && v != 1) return fail("decode mode must be 0 or 1"); e->decode_mode = (int)v; break;
+    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 2) return fail("decode mode must be 0, 1 or 2"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM: if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1"); e->prefill_gemm = (int)v; break;
-    case T2S_OPT_NUM_CTAS: if (v < 0 || v > 1024) return fail("num_ctas out of range"); e->num_ctas = (int)v; break;
-    case T2S_OPT_DETERMINISTIC: if (v != 0 && v != 1) return fail("deterministic must be 0 or 1"); e->deterministic = (int)v; break;
+    case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
   }
@@ -396,6 +399,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   int rc = 0;
   rc |= e->ints.ensure(n_ints * 4);
   rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
+  rc |= e->kvoff.ensure(R * 8);
   rc |= e->x0_rows.ensure((size_t)T * D * 4);
   rc |= e->q.ensure(R * D * 4);
   rc |= e->attn.ensure(R * D * 2);
@@ -424,6 +428,10 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   o = (o + 3) & ~(size_t)3;
   const size_t o_qt = put(reinterpret_cast<const int*>(qtiles.data()), qtiles.size() * 4);
   CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
+  std::vector<long long> kvoff(T);
+  for (int r = 0; r < T; ++r)
+    kvoff[r] = ((long long)page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> 6)] * PAGE + (row_pos[r] & (PAGE - 1))) * D;
+  CK(cudaMemcpyAsync(e->kvoff.p, kvoff.data(), (size_t)T * 8, cudaMemcpyHostToDevice, s));
   int* di = e->ints.as<int>();
   e->d_row_slot = di + o_row_slot; e->d_row_pos = di + o_row_pos; e->d_head_rows = di + o_head;
   e->d_text_off = di + o_toff; e->d_text_len = di + o_tlen; e->d_s0 = di + o_s0;
@@ -477,7 +485,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
   c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
   c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
-  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len; c.deterministic = e->deterministic;
+  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
   c.kpool = e->kpool.as<bf16>(); c.vpool = e->vpool.as<bf16>();
   c.kv_layer_stride = e->pool_pages * PAGE * D;
   c.page_table = e->d_page_table; c.max_pages = max_pages;
@@ -486,10 +494,13 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.bar = reinterpret_cast<unsigned*>(i2 + 4);
   c.stats = reinterpret_cast<unsigned long long*>(i2 + 8);  // 3 x u64, 8-byte aligned
   c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
-  c.row_slot = e->d_row_slot; c.row_pos = e->d_row_pos;
+  c.row_slot = e->d_row_slot; c.row_pos = e->d_row_pos; c.row_kvoff = e->kvoff.as<long long>();
   c.q = e->q.as<float>(); c.attn = e->attn.as<bf16>(); c.y1 = e->y1.as<float>(); c.h = e->h.as<bf16>();
   c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>(); c.logits = e->logits.as<float>();
   c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
+  c.attn_desc = e->attn_desc.as<int>();
+  c.attn_ctas = (e->decode_mode == 1 && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
+  c.probe = e->probe;
   c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
   c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
   c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
@@ -497,6 +508,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
   c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
   c.seen = e->seen.as<uint32_t>();
+  c.timeline = e->timeline; c.tl_step = e->tl_step; c.tl_slots = e->tl_slots;
   e->cp = c; e->cp.x0 = e->x0_rows.as<float>(); e->cp.x0_by_slot = 0; e->cp.head_rows = e->d_head_rows;
   e->cd = c; e->cd.x0 = e->x0_slots.as<float>(); e->cd.x0_by_slot = 1; e->cd.head_rows = nullptr;
   const Ctx& cp = e->cp;
@@ -561,11 +573,11 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   CK(cudaEventRecord(e->ev0, s));
   if (n_active > 0 && budget > 0) {
     if (e->decode_mode == 1) {
-      int grid = e->num_ctas > 0 ? e->num_ctas : e->num_sms;
+      int grid = e->cd.attn_ctas;
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_persistent, NT, SMEM_MAX));
       if (per_sm < 1) return fail("t2s_decode: persistent kernel does not fit on an SM");
-      grid = std::min(grid, per_sm * e->num_sms);
+      if (grid > per_sm * e->num_sms) return fail("t2s_decode: %d CTAs cannot be co-resident", grid);
       CK(cudaMemsetAsync(e->cd.bar, 0, 4, s));
       Ctx c = e->cd;
       int steps = budget;
@@ -574,7 +586,7 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
       e->launches++;
     } else {
       // one graph = one decode step (122 kernel nodes); re-captured only when the context changes
-      if (!e->graph_exec || memcmp(&e->graph_ctx, &e->cd, sizeof(Ctx)) != 0) {
+      if (e->decode_mode == 0 && (!e->graph_exec || memcmp(&e->graph_ctx, &e->cd, sizeof(Ctx)) != 0)) {
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
         cudaStream_t cs;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -595,8 +607,12 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
       int done_steps = 0;
       while (done_steps < budget && n_active > 0) {
         const int chunk = std::min(e->check_steps, budget - done_steps);
-        for (int i = 0; i < chunk; ++i) CK(cudaGraphLaunch(e->graph_exec, s));
-        e->launches += (long long)chunk * e->nodes_per_step;
+        if (e->decode_mode == 2) {  // plain stream launches, no graph (profiling aid)
+          for (int i = 0; i < chunk; ++i) launch_decode_step(e, e->cd, s);
+        } else {
+          for (int i = 0; i < chunk; ++i) CK(cudaGraphLaunch(e->graph_exec, s));
+          e->launches += (long long)chunk * e->nodes_per_step;
+        }
         done_steps += chunk;
         CK(cudaMemcpyAsync(e->h_pinned, e->cd.n_rows, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -711,6 +727,31 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   CK(cudaMemcpy2DAsync(tok_out, 4, c.sampled + step, (size_t)ms * 4, 4, n, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpy2DAsync(greedy_out, 4, c.greedy_rec + step, (size_t)ms * 4, 4, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots, long long* probe) {
+  if (!e) return fail("null engine");
+  e->timeline = buf; e->tl_step = step; e->tl_slots = buf ? slots : 0; e->probe = buf ? probe : nullptr;
+  return 0;
+}
+
+extern "C" int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* ms_out, void* stream_) {
+  if (!e || !ms_out || n_barriers < 1) return fail("t2s_bench_barrier: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  if (e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4)) return 1;
+  int* i2 = e->ints2.as<int>();
+  CK(cudaMemsetAsync(i2, 0, 64, s));
+  unsigned* bar = reinterpret_cast<unsigned*>(i2 + 4);
+  int* ab = i2 + 3;
+  int grid = n_ctas > 0 ? n_ctas : e->num_sms;
+  void* args[] = {&bar, &ab, &n_barriers};
+  CK(cudaEventRecord(e->ev0, s));
+  CK(cudaLaunchCooperativeKernel((const void*)k_barrier_bench, dim3(grid), dim3(NT), args, 0, s));
+  CK(cudaEventRecord(e->ev1, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
+  e->launches++;
   return 0;
 }
 

@@ -5,7 +5,7 @@
 
 namespace t2s {
 
-constexpr size_t SMEM_PROJ = sizeof(ProjSmem);
+constexpr size_t SMEM_PROJ = SMEM_PROJ_MAX;
 constexpr size_t SMEM_ATTN = sizeof(AttnSmem);
 constexpr size_t SMEM_SAMP = sizeof(SampSmem);
 constexpr size_t SMEM_MAX = SMEM_PROJ > SMEM_ATTN ? (SMEM_PROJ > SMEM_SAMP ? SMEM_PROJ : SMEM_SAMP)
@@ -19,17 +19,17 @@ __global__ void __launch_bounds__(NT, 1) k_phase(Ctx c, int layer) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int cta = blockIdx.x, ncta = gridDim.x;
   if (PH == PH_QKV) {
-    phase_qkv(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+    phase_qkv(c, layer, ld_cg_i(c.n_rows), cta, ncta, smem);
   } else if (PH == PH_ATTN) {
     phase_attn_decode(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<AttnSmem*>(smem));
   } else if (PH == PH_OPROJ) {
-    phase_oproj(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+    phase_oproj(c, layer, ld_cg_i(c.n_rows), cta, ncta, smem);
   } else if (PH == PH_FFN1) {
-    phase_ffn1(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+    phase_ffn1(c, layer, ld_cg_i(c.n_rows), cta, ncta, smem);
   } else if (PH == PH_FFN2) {
-    phase_ffn2(c, layer, ld_cg_i(c.n_rows), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+    phase_ffn2(c, layer, ld_cg_i(c.n_rows), cta, ncta, smem);
   } else if (PH == PH_HEAD) {
-    phase_head(c, ld_cg_i(c.n_active), cta, ncta, *reinterpret_cast<ProjSmem*>(smem));
+    phase_head(c, ld_cg_i(c.n_active), cta, ncta, smem);
   } else if (PH == PH_SAMPLE) {
     phase_sample(c, ld_cg_i(c.n_active), cta, ncta, *reinterpret_cast<SampSmem*>(smem));
   } else if (PH == PH_PLAN) {
@@ -46,31 +46,50 @@ __global__ void __launch_bounds__(NT, 1) k_decode_persistent(Ctx c, int max_new_
   const int cta = blockIdx.x, ncta = gridDim.x;
   GridBarrier bar;
   bar.init(c.bar, c.abort_flag, (unsigned)ncta);
-  ProjSmem& ps = *reinterpret_cast<ProjSmem*>(smem);
   AttnSmem& as = *reinterpret_cast<AttnSmem*>(smem);
   SampSmem& ss = *reinterpret_cast<SampSmem*>(smem);
   for (int it = 0; it < max_new_steps; ++it) {
     const int n = ld_cg_i(c.n_active);
     if (n == 0 || __ldcg(c.abort_flag) != 0) break;
+    if (c.timeline) {
+      const bool on = (it == c.tl_step);
+      bar.tl = on ? c.timeline + (size_t)cta * c.tl_slots * 2 : nullptr;
+      bar.tl_k = 0; bar.tl_n = c.tl_slots;
+    }
     for (int layer = 0; layer < c.n_layer; ++layer) {
-      phase_qkv(c, layer, n, cta, ncta, ps);
+      const bool probing = c.probe && bar.tl && layer == 1;
+      Probe p1{probing ? c.probe + (size_t)cta * 64 : nullptr, 0};
+      Probe p2{probing ? c.probe + (size_t)cta * 64 + 32 : nullptr, 0};
+      phase_qkv(c, layer, n, cta, ncta, smem, &p1);
+      prefetch_phase(c, PF_WO, layer, cta);  // attention has no weights: fetch the O-projection slice early
       bar.sync();
-      phase_attn_decode(c, layer, n, cta, ncta, as);
+      phase_attn_decode(c, layer, n, cta, ncta, as, &p2);
+      prefetch_phase(c, PF_W1, layer, cta);
       bar.sync();
-      phase_oproj(c, layer, n, cta, ncta, ps);
+      phase_oproj(c, layer, n, cta, ncta, smem);
+      prefetch_phase(c, PF_W2, layer, cta);
       bar.sync();
-      phase_ffn1(c, layer, n, cta, ncta, ps);
+      phase_ffn1(c, layer, n, cta, ncta, smem);
+      prefetch_phase(c, PF_WQKV_NEXT, layer, cta);  // next layer's QKV slice, or the head's after the last layer
       bar.sync();
-      phase_ffn2(c, layer, n, cta, ncta, ps);
+      phase_ffn2(c, layer, n, cta, ncta, smem);
       bar.sync();
     }
-    phase_head(c, n, cta, ncta, ps);
+    phase_head(c, n, cta, ncta, smem);
     bar.sync();
     phase_sample(c, n, cta, ncta, ss);
+    if (cta < 3 * D / 16) prefetch_unit(c.wmat + OFF_WQKV, cta, D, 1);  // layer 0 of the next step
     bar.sync();
     if (cta == 0) phase_plan(c, reinterpret_cast<int*>(smem));
     bar.sync();
   }
+}
+
+// Grid-barrier latency microbenchmark (measurement hook): n barriers back to back.
+__global__ void __launch_bounds__(NT, 1) k_barrier_bench(unsigned* counter, int* abort_flag, int n) {
+  GridBarrier bar;
+  bar.init(counter, abort_flag, gridDim.x);
+  for (int i = 0; i < n; ++i) bar.sync();
 }
 
 // ---- session initialisation ----------------------------------------------------------------------------
@@ -141,9 +160,9 @@ __global__ void k_bert_rows(bf16* out, const void* const* bert, const long long*
 __global__ void __launch_bounds__(NT, 1) k_bert_proj(Ctx c, const bf16* bert_rows, const int* trow_row, int n_text_rows) {
   extern __shared__ __align__(16) unsigned char smem[];
   ProjArgs a{};
-  a.w = c.wbert; a.n_tiles = D / 16; a.k_slices = BERT / 512; a.k_seq = BERT / 512;
-  a.in_b16 = bert_rows; a.in_stride = BERT; a.out_idx = trow_row;
-  proj_phase<IN_BF16, OUT_BERT>(c, a, n_text_rows, blockIdx.x, gridDim.x, *reinterpret_cast<ProjSmem*>(smem));
+  a.w = c.wbert; a.n_tiles = D / 16;
+  a.in_b16 = bert_rows; a.out_idx = trow_row;
+  proj_phase<IN_BF16, OUT_BERT, 8, 1>(c, a, n_text_rows, blockIdx.x, gridDim.x, smem);
 }
 
 // ---- prefill attention with the prefix-LM mask (t2s_model.py:644-683 + SDPA :157) ------------------------

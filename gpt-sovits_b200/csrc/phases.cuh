@@ -10,31 +10,48 @@
 
 namespace t2s {
 
+// measurement hook: thread 0 records SM clocks at named points of one phase instance
+struct Probe {
+  long long* buf;
+  int k;
+  __device__ __forceinline__ void mark() {
+    if (buf && threadIdx.x == 0 && k < 32) buf[k++] = clock64();
+  }
+};
+
 // =====================================================================================================
 // Skinny projections  Y[rows, features] = act(X[rows, K]) * W[features, K]^T
 //
-// Work unit = (16-feature tile, 512-wide K slice): its weights are one contiguous 16 KB block stored
-// in m16n8k16 A-fragment order, so a warp loads a fragment with one coalesced 128-bit load per lane.
-// Inside a unit the 8 warps split K (4 k-blocks each), rows are processed in tiles of 32 (4 MMA
-// n-tiles), partial sums are reduced across warps in shared memory, and the epilogue is fused.
-// Units are spread over all CTAs, so every SM streams a disjoint slice of the weights.
+// Work unit = one 16-feature tile over the whole K: its weights are one contiguous block (16 KB for
+// K=512, 64 KB for K=2048) stored in m16n8k16 A-fragment order, so a warp loads a fragment with one
+// coalesced 128-bit load per lane.  Inside a unit the 8 warps split K (KBW k-blocks each), rows are
+// processed in tiles of 32 (4 MMA n-tiles), the warps' partial sums are reduced in shared memory in a
+// fixed order (no floating-point atomics anywhere: results are bit-reproducible) and the epilogue is
+// fused.  Units are spread over all CTAs, so every SM streams a disjoint slice of the weights; the next
+// phase's slice is prefetched into L2 before the grid barrier (prefetch_unit).
 // =====================================================================================================
 enum { IN_X0 = 0, IN_LN = 1, IN_BF16 = 2 };
 enum { OUT_QKV = 0, OUT_O = 1, OUT_FFN1 = 2, OUT_FFN2 = 3, OUT_HEAD = 4, OUT_BERT = 5 };
 
-struct ProjSmem {
-  bf16 xs[RT * XS];
-  float red[NW][16][RT + 1];
+// shared-memory carve-up for a projection with KBW k-blocks per warp (K = KBW*128)
+template <int KBW, int TPC = 1>
+struct ProjLayout {
+  static constexpr int K = KBW * 128;
+  static constexpr int XSK = K + 8;  // bf16 row stride: (K+8)/2 words = 4 mod 32 -> conflict-free B fragments
+  static constexpr size_t XS_BYTES = (size_t)RT * XSK * 2;
+  static constexpr size_t RED_BYTES = (size_t)NW * 16 * TPC * (RT + 1) * 4;
+  static constexpr size_t BYTES = XS_BYTES + RED_BYTES + RT * 8;
+  __device__ static bf16* xs(unsigned char* base) { return reinterpret_cast<bf16*>(base); }
+  __device__ static float* red(unsigned char* base) { return reinterpret_cast<float*>(base + XS_BYTES); }
+  __device__ static long long* kvoff(unsigned char* base) { return reinterpret_cast<long long*>(base + XS_BYTES + RED_BYTES); }
 };
+constexpr size_t SMEM_PROJ_MAX = ProjLayout<16, 1>::BYTES > ProjLayout<4, 2>::BYTES ? ProjLayout<16, 1>::BYTES : ProjLayout<4, 2>::BYTES;
 
 struct ProjArgs {
   const bf16* w;       // packed weights of this matrix
   int n_tiles;         // 16-feature tiles
-  int k_slices;        // 512-wide K slices per feature row
-  int k_seq;           // slices accumulated sequentially inside one unit (k_slices/k_seq units run in parallel)
   const float* in_f32; // IN_X0 / IN_LN source rows [.,D]
-  const bf16* in_b16;  // IN_BF16 source rows
-  int in_stride;       // IN_BF16 row stride (elements)
+  const bf16* in_b16;  // IN_BF16 source rows [., K]
   const int* in_idx;   // optional row gather for the fp32 sources
   const float* ln_g;   // IN_LN
   const float* ln_b;
@@ -47,40 +64,67 @@ struct ProjArgs {
   int layer;
 };
 
-template <int IN, int OUT>
-__device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, ProjSmem& sm, int r0, int n_rows,
-                                           int nt, int ks, const float (&g)[16], const float (&be)[16]) {
+// L2 prefetch of one unit's weight block (issued before a grid barrier for the NEXT phase)
+__device__ __forceinline__ void prefetch_unit(const bf16* w, int u, int k, int tpc) {
+  const size_t bytes = (size_t)16 * tpc * k * 2;  // (the head's last unit over-reads into its zero padding)
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(w) + (size_t)u * bytes;
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)NT * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
+template <int IN, int OUT, int KBW, int TPC>
+__device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, unsigned char* smem, int r0, int n_rows,
+                                           int u, const float (&g)[16], const float (&be)[16]) {
+  using LY = ProjLayout<KBW, TPC>;
+  bf16* xs = LY::xs(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (OUT == OUT_QKV && threadIdx.x < RT) {
+    const int r = r0 + threadIdx.x;
+    LY::kvoff(smem)[threadIdx.x] = (r < n_rows) ? __ldcg(c.row_kvoff + r) : 0ll;
+  }
+  if (IN == IN_BF16) {
+    constexpr int CPL = LY::K / 256;               // 16-byte chunks per lane per row
+    constexpr int RG = (16 / CPL) < 4 ? (16 / CPL) : 4;  // rows in flight per warp
 #pragma unroll
-  for (int i = 0; i < RT / NW; ++i) {
-    const int rl = warp + NW * i;
-    const int r = r0 + rl;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.xs + rl * XS);
-    if (r >= n_rows) {
+    for (int i0 = 0; i0 < RT / NW; i0 += RG) {
+      uint4 v[RG][CPL];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dst[(lane * 4 + 128 * j) / 2] = 0u;
-        dst[(lane * 4 + 128 * j) / 2 + 1] = 0u;
+      for (int i = 0; i < RG; ++i) {
+        const int r = r0 + warp + NW * (i0 + i);
+        const bf16* src = a.in_b16 + (size_t)r * LY::K;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) v[i][j] = (r < n_rows) ? ld_cg16(src + (lane + 32 * j) * 8) : make_uint4(0, 0, 0, 0);
       }
-      continue;
+#pragma unroll
+      for (int i = 0; i < RG; ++i) {
+        const int rl = warp + NW * (i0 + i);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) *reinterpret_cast<uint4*>(xs + rl * LY::XSK + (lane + 32 * j) * 8) = v[i][j];
+      }
     }
-    if (IN == IN_BF16) {
-      const bf16* src = a.in_b16 + (size_t)r * a.in_stride + ks * 512;
+  } else {
+    // fp32 sources are always 512 wide: issue every load of this warp's 4 rows, then normalise
+    constexpr int NR = RT / NW;
+    int ri[NR];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 v = ld_cg16(src + (lane + 32 * j) * 8);
-        *reinterpret_cast<uint4*>(sm.xs + rl * XS + (lane + 32 * j) * 8) = v;
-      }
-    } else {
-      const int ri = a.in_idx ? ld_cg_i(a.in_idx + r) : r;
-      const float* src = a.in_f32 + (size_t)ri * D;
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + warp + NW * i;
+      ri[i] = (r < n_rows) ? (a.in_idx ? ld_cg_i(a.in_idx + r) : r) : -1;
+    }
+    float4 raw[NR][4];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        raw[i][j] = (ri[i] >= 0) ? ld_cg_f4(a.in_f32 + (size_t)ri[i] * D + lane * 4 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int rl = warp + NW * i, r = r0 + rl;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(xs + rl * LY::XSK);
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 t = ld_cg_f4(src + lane * 4 + 128 * j);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-      }
-      if (IN == IN_LN) {
+      for (int j = 0; j < 4; ++j) { v[4 * j] = raw[i][j].x; v[4 * j + 1] = raw[i][j].y; v[4 * j + 2] = raw[i][j].z; v[4 * j + 3] = raw[i][j].w; }
+      if (IN == IN_LN && ri[i] >= 0) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) s += v[j];
@@ -91,16 +135,22 @@ __device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, Proj
         const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / D) + LN_EPS);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = (v[j] - mean) * rstd * g[j] + be[j];
-        if (OUT == OUT_QKV && nt == 0 && lane == 0) c.stat2[r] = make_float2(mean, rstd);
-        if (OUT == OUT_FFN1 && lane == (nt & 31)) {
-          // y2 := LN1(y1) + b2 on this unit's 4-feature slice; FFN2 adds its split-K partials atomically
-          const int j = nt >> 5;
-          const float4 bb = *reinterpret_cast<const float4*>(a.b2 + 4 * nt);
-          float4 o;
+        if (OUT == OUT_QKV && u == 0 && lane == 0) c.stat2[r] = make_float2(mean, rstd);
+        if (OUT == OUT_FFN1) {
+          // y2 := LN1(y1) + b2 on this unit's 4-feature slices (one per tile); FFN2 then adds its product
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            if (jj == j) o = make_float4(v[4 * jj] + bb.x, v[4 * jj + 1] + bb.y, v[4 * jj + 2] + bb.z, v[4 * jj + 3] + bb.w);
-          *reinterpret_cast<float4*>(c.y2 + (size_t)r * D + 4 * nt) = o;
+          for (int tt = 0; tt < TPC; ++tt) {
+            const int nt = u * TPC + tt;
+            if (lane == (nt & 31)) {
+              const int j = nt >> 5;
+              const float4 bb = *reinterpret_cast<const float4*>(a.b2 + 4 * nt);
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (jj == j) o = make_float4(v[4 * jj] + bb.x, v[4 * jj + 1] + bb.y, v[4 * jj + 2] + bb.z, v[4 * jj + 3] + bb.w);
+              *reinterpret_cast<float4*>(c.y2 + (size_t)r * D + 4 * nt) = o;
+            }
+          }
         }
       }
 #pragma unroll
@@ -113,15 +163,14 @@ __device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, Proj
 }
 
 template <int OUT>
-__device__ __forceinline__ void proj_epilogue(const Ctx& c, const ProjArgs& a, int r, int f, float acc) {
+__device__ __forceinline__ void proj_epilogue(const Ctx& c, const ProjArgs& a, const long long* kvoff, int r, int rl,
+                                              int f, float acc, float bias, float resg, float resb) {
   if (OUT == OUT_QKV) {
-    const float val = acc + a.bias[f];
+    const float val = acc + bias;
     if (f < D) {
       c.q[(size_t)r * D + f] = val * QSCALE;
     } else {
-      const int slot = ld_cg_i(c.row_slot + r), pos = ld_cg_i(c.row_pos + r);
-      const int page = c.page_table[slot * c.max_pages + (pos >> 6)];
-      const size_t off = (size_t)a.layer * c.kv_layer_stride + ((size_t)page * PAGE + (pos & (PAGE - 1))) * D;
+      const size_t off = (size_t)a.layer * c.kv_layer_stride + (size_t)kvoff[rl];
       if (f < 2 * D) c.kpool[off + (f - D)] = __float2bfloat16_rn(val);
       else c.vpool[off + (f - 2 * D)] = __float2bfloat16_rn(val);
     }
@@ -132,30 +181,35 @@ __device__ __forceinline__ void proj_epilogue(const Ctx& c, const ProjArgs& a, i
       res = ld_cg_f(c.x0 + (size_t)ri * D + f);
     } else {
       const float2 st = __ldcg(c.stat2 + r);
-      res = (ld_cg_f(c.y2 + (size_t)r * D + f) - st.x) * st.y * a.res_g[f] + a.res_b[f];
+      res = (ld_cg_f(c.y2 + (size_t)r * D + f) - st.x) * st.y * resg + resb;
     }
-    c.y1[(size_t)r * D + f] = res + a.bias[f] + acc;
+    c.y1[(size_t)r * D + f] = res + bias + acc;
   } else if (OUT == OUT_FFN1) {
-    c.h[(size_t)r * FF + f] = __float2bfloat16_rn(fmaxf(acc + a.bias[f], 0.f));
+    c.h[(size_t)r * FF + f] = __float2bfloat16_rn(fmaxf(acc + bias, 0.f));
   } else if (OUT == OUT_FFN2) {
     float* p = c.y2 + (size_t)r * D + f;
-    if (a.k_seq == a.k_slices) *p = __ldcg(p) + acc;  // single writer: deterministic
-    else atomicAdd(p, acc);                           // split-K across CTAs
+    *p = __ldcg(p) + acc;  // y2 was initialised to LN1(y1) + b2 by FFN1's staging; single writer
   } else if (OUT == OUT_HEAD) {
     if (f < V) c.logits[(size_t)r * VPAD + f] = acc;
   } else if (OUT == OUT_BERT) {
     float* p = c.x0 + (size_t)a.out_idx[r] * D + f;
-    if (a.k_seq == a.k_slices) *p = __ldcg(p) + acc;
-    else atomicAdd(p, acc);
+    *p = __ldcg(p) + acc;
   }
 }
 
-template <int IN, int OUT>
-__device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta, int ncta, ProjSmem& sm) {
+// TPC = 16-feature tiles per unit (per CTA): 2 halves the number of CTAs that re-read every activation
+// row (the L2 broadcast is what bounds the staging step at batch >= 16) at no cost in weight bytes.
+template <int IN, int OUT, int KBW, int TPC>
+__device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta, int ncta, unsigned char* smem,
+                           Probe* pr = nullptr) {
+  using LY = ProjLayout<KBW, TPC>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int n_units = a.n_tiles * (a.k_slices / a.k_seq);
-  const int kb_per_row = a.k_slices * 32;
+  constexpr int KB_ROW = KBW * NW;  // k-blocks per feature tile
+  constexpr int FU = 16 * TPC;      // features per unit
+  bf16* xs = LY::xs(smem);
+  float (*red)[FU][RT + 1] = reinterpret_cast<float (*)[FU][RT + 1]>(LY::red(smem));
+  const long long* kvoff = LY::kvoff(smem);
   float lg[16], lb[16];
   if (IN == IN_LN) {
 #pragma unroll
@@ -169,114 +223,169 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
 #pragma unroll
     for (int j = 0; j < 16; ++j) { lg[j] = 1.f; lb[j] = 0.f; }
   }
+  if (pr) pr->mark();
+  const int n_units = (a.n_tiles + TPC - 1) / TPC;
   for (int u = cta; u < n_units; u += ncta) {
-    const int nt = u % a.n_tiles, kp = u / a.n_tiles;
+    // this warp's A fragments (k-blocks warp*KBW .. +KBW-1 of each feature tile), loaded once per unit
+    uint4 af[TPC][KBW];
+#pragma unroll
+    for (int tt = 0; tt < TPC; ++tt) {
+      const int nt = min(u * TPC + tt, a.n_tiles - 1);  // a ragged last unit re-reads a valid tile (result discarded)
+      const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * KB_ROW + warp * KBW) * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < KBW; ++i) af[tt][i] = ld_weight16(wp + i * 32);
+    }
+    // per-thread epilogue constants: this thread always reduces feature u*FU + (tid % FU)
+    const int fme = u * FU + (threadIdx.x % FU);
+    const bool fok = fme < a.n_tiles * 16;
+    const float bias = (a.bias && fok) ? a.bias[fme] : 0.f;
+    const float resg = (OUT == OUT_O && a.res_g) ? a.res_g[fme] : 1.f;
+    const float resb = (OUT == OUT_O && a.res_b) ? a.res_b[fme] : 0.f;
     for (int r0 = 0; r0 < n_rows; r0 += RT) {
       const int rows_here = min(RT, n_rows - r0);
       const int n8 = (rows_here + 7) >> 3;
-      float acc[4][4];
+      __syncthreads();  // previous readers of xs / red / kvoff are done
+      if (pr) pr->mark();
+      proj_stage<IN, OUT, KBW, TPC>(c, a, smem, r0, n_rows, u, lg, lb);
+      __syncthreads();
+      if (pr) pr->mark();
+      float acc[TPC][4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int tt = 0; tt < TPC; ++tt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int kq = 0; kq < a.k_seq; ++kq) {
-        const int ks = kp * a.k_seq + kq;
-        // this warp's 4 A fragments (k-blocks ks*32 + warp*4 .. +3 of feature tile nt)
-        uint4 af[4];
-        const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * kb_per_row + ks * 32 + warp * 4) * 32 + lane;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = ld_weight16(wp + i * 32);
-        __syncthreads();  // previous readers of xs / red are done
-        proj_stage<IN, OUT>(c, a, sm, r0, n_rows, nt, ks, lg, lb);
-        __syncthreads();
+          for (int j = 0; j < 4; ++j) acc[tt][i][j] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k0 = (warp * 4 + i) * 16;
+      for (int i = 0; i < KBW; ++i) {
+        const int k0 = (warp * KBW + i) * 16;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            if (n < n8) {
-              const uint32_t* xr = reinterpret_cast<const uint32_t*>(sm.xs + (n * 8 + g) * XS + k0);
-              mma_bf16_16816(acc[n], af[i], xr[t], xr[4 + t]);
-            }
+        for (int n = 0; n < 4; ++n) {
+          if (n < n8) {
+            const uint32_t* xr = reinterpret_cast<const uint32_t*>(xs + (n * 8 + g) * LY::XSK + k0);
+            const uint32_t b0 = xr[t], b1 = xr[4 + t];
+#pragma unroll
+            for (int tt = 0; tt < TPC; ++tt) mma_bf16_16816(acc[tt][n], af[tt][i], b0, b1);
           }
         }
       }
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        sm.red[warp][g][n * 8 + 2 * t] = acc[n][0];
-        sm.red[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
-        sm.red[warp][g + 8][n * 8 + 2 * t] = acc[n][2];
-        sm.red[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
-      }
+      for (int tt = 0; tt < TPC; ++tt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          red[warp][tt * 16 + g][n * 8 + 2 * t] = acc[tt][n][0];
+          red[warp][tt * 16 + g][n * 8 + 2 * t + 1] = acc[tt][n][1];
+          red[warp][tt * 16 + g + 8][n * 8 + 2 * t] = acc[tt][n][2];
+          red[warp][tt * 16 + g + 8][n * 8 + 2 * t + 1] = acc[tt][n][3];
+        }
       __syncthreads();
+      if (pr) pr->mark();
+      if (fok) {
 #pragma unroll
-      for (int o = threadIdx.x; o < 16 * RT; o += NT) {
-        const int fl = o & 15, n = o >> 4;
-        if (n < rows_here) {
-          float s = 0.f;
+        for (int o = threadIdx.x; o < FU * RT; o += NT) {
+          const int fl = o % FU, n = o / FU;
+          if (n < rows_here) {
+            float s = 0.f;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) s += sm.red[w][fl][n];
-          proj_epilogue<OUT>(c, a, r0 + n, nt * 16 + fl, s);
+            for (int w = 0; w < NW; ++w) s += red[w][fl][n];
+            proj_epilogue<OUT>(c, a, kvoff, r0 + n, n, u * FU + fl, s, bias, resg, resb);
+          }
         }
       }
+      if (pr) pr->mark();
     }
   }
 }
 
 // ---- the five per-layer projection phases + head, with their argument wiring ------------------------
-__device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
+__device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm,
+                                          Probe* pr = nullptr) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WQKV;
-  a.n_tiles = 3 * D / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
+  a.n_tiles = 3 * D / 16; a.layer = layer;
   a.bias = c.wvec + (size_t)layer * LV + VO_BQKV;
   if (layer == 0) {
     a.in_f32 = c.x0; a.in_idx = c.x0_by_slot ? c.row_slot : nullptr;
-    proj_phase<IN_X0, OUT_QKV>(c, a, n_rows, cta, ncta, sm);
+    proj_phase<IN_X0, OUT_QKV, 4, 1>(c, a, n_rows, cta, ncta, sm, pr);
   } else {
     a.in_f32 = c.y2;
     a.ln_g = c.wvec + (size_t)(layer - 1) * LV + VO_G2;
     a.ln_b = c.wvec + (size_t)(layer - 1) * LV + VO_BE2;
-    proj_phase<IN_LN, OUT_QKV>(c, a, n_rows, cta, ncta, sm);
+    proj_phase<IN_LN, OUT_QKV, 4, 1>(c, a, n_rows, cta, ncta, sm, pr);
   }
 }
-__device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
+__device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WO;
-  a.n_tiles = D / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
-  a.in_b16 = c.attn; a.in_stride = D;
+  a.n_tiles = D / 16; a.layer = layer;
+  a.in_b16 = c.attn;
   a.bias = c.wvec + (size_t)layer * LV + VO_BO;
   if (layer > 0) {
     a.res_g = c.wvec + (size_t)(layer - 1) * LV + VO_G2;
     a.res_b = c.wvec + (size_t)(layer - 1) * LV + VO_BE2;
   }
-  proj_phase<IN_BF16, OUT_O>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<IN_BF16, OUT_O, 4, 1>(c, a, n_rows, cta, ncta, sm);
 }
-__device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
+__device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W1;
-  a.n_tiles = FF / 16; a.k_slices = 1; a.k_seq = 1; a.layer = layer;
+  a.n_tiles = FF / 16; a.layer = layer;
   a.in_f32 = c.y1;
   a.ln_g = c.wvec + (size_t)layer * LV + VO_G1;
   a.ln_b = c.wvec + (size_t)layer * LV + VO_BE1;
   a.bias = c.wvec + (size_t)layer * LV + VO_B1;
   a.b2 = c.wvec + (size_t)layer * LV + VO_B2;
-  proj_phase<IN_LN, OUT_FFN1>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<IN_LN, OUT_FFN1, 4, 1>(c, a, n_rows, cta, ncta, sm);
 }
-__device__ __forceinline__ void phase_ffn2(const Ctx& c, int layer, int n_rows, int cta, int ncta, ProjSmem& sm) {
+__device__ __forceinline__ void phase_ffn2(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W2;
-  a.n_tiles = D / 16; a.k_slices = FF / 512; a.k_seq = c.deterministic ? FF / 512 : 1; a.layer = layer;
-  a.in_b16 = c.h; a.in_stride = FF;
-  proj_phase<IN_BF16, OUT_FFN2>(c, a, n_rows, cta, ncta, sm);
+  a.n_tiles = D / 16; a.layer = layer;
+  a.in_b16 = c.h;
+  proj_phase<IN_BF16, OUT_FFN2, 16, 1>(c, a, n_rows, cta, ncta, sm);
 }
-__device__ __forceinline__ void phase_head(const Ctx& c, int n_rows, int cta, int ncta, ProjSmem& sm) {
+__device__ __forceinline__ void phase_head(const Ctx& c, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.whead;
-  a.n_tiles = VT; a.k_slices = 1; a.k_seq = 1; a.layer = c.n_layer;
+  a.n_tiles = VT; a.layer = c.n_layer;
   a.in_f32 = c.y2; a.in_idx = c.head_rows;
   a.ln_g = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_G2;
   a.ln_b = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_BE2;
-  proj_phase<IN_LN, OUT_HEAD>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<IN_LN, OUT_HEAD, 4, 1>(c, a, n_rows, cta, ncta, sm);
+}
+
+// L2 prefetch of this CTA's K/V position ranges of `layer` (issued during the QKV phase, one grid barrier
+// before the attention phase reads them): one bulk-prefetch instruction per page run.
+__device__ __forceinline__ void prefetch_kv(const Ctx& c, int layer, int cta) {
+  const int tid = threadIdx.x;
+  const int e = tid >> 7, i = tid & 127;  // descriptor entry, page-run index
+  const int4 ds = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
+  if (ds.x < 0) return;
+  const int pbeg = ds.y, pend = ds.z;
+  const int p0 = (pbeg & ~(PAGE - 1)) + (i >> 1) * PAGE;  // page-aligned run start; even i: K, odd i: V
+  if (p0 >= pend) return;
+  const int a0 = max(p0, pbeg), a1 = min(p0 + PAGE, pend);
+  const int slot = ld_cg_i(c.row_slot + ds.x);
+  const int page = c.page_table[slot * c.max_pages + (a0 >> 6)];
+  const bf16* base = ((i & 1) ? c.vpool : c.kpool) + (size_t)layer * c.kv_layer_stride +
+                     ((size_t)page * PAGE + (a0 & (PAGE - 1))) * D;
+  const unsigned bytes = (unsigned)(a1 - a0) * D * 2;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
+}
+
+// L2 prefetch of the weights this CTA will need in the phase AFTER the coming one (called right before a
+// grid barrier so HBM latency overlaps the barrier and the next phase).  `next` = the phase about to be
+// entered after the barrier is `cur + 1`; we prefetch for cur + 2's projection when cur + 1 has no weights.
+enum { PF_WO = 0, PF_W1 = 1, PF_W2 = 2, PF_WQKV_NEXT = 3, PF_HEAD = 4 };
+__device__ __forceinline__ void prefetch_phase(const Ctx& c, int what, int layer, int cta) {
+  const bf16* wl = c.wmat + (size_t)layer * LW;
+  if (what == PF_WO) { if (cta < D / 16) prefetch_unit(wl + OFF_WO, cta, D, 1); }
+  else if (what == PF_W1) { if (cta < FF / 16) prefetch_unit(wl + OFF_W1, cta, D, 1); }
+  else if (what == PF_W2) { if (cta < D / 16) prefetch_unit(wl + OFF_W2, cta, FF, 1); }
+  else if (what == PF_WQKV_NEXT) {
+    if (layer + 1 < c.n_layer) { if (cta < 3 * D / 16) prefetch_unit(wl + LW + OFF_WQKV, cta, D, 1); }
+    else if (cta < VT) prefetch_unit(c.whead, cta, D, 1);
+  }
 }
 
 // =====================================================================================================
@@ -393,54 +502,18 @@ __device__ __forceinline__ void attn_segment(const Ctx& c, int layer, int slot, 
   }
 }
 
-__device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, int ncta, AttnSmem& sm) {
+// The split-KV work assignment is the same for all layers of a step, so phase_plan computes it once:
+// every CTA gets at most two descriptors {row, pbeg, pend, (j << 16) | count}: its j-th of `count`
+// position ranges of `row`.  A row's partials live in c.part[first_cta .. first_cta + count).
+__device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, int ncta, AttnSmem& sm, Probe* pr = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- 1. chunk size from the total number of cached positions
-  int np = (tid < n_rows) ? ld_cg_i(c.row_pos + tid) + 1 : 0;
-  int tot = np;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if (lane == 0) sm.scratch[warp] = tot;
-  __syncthreads();
-  int total_pos = 0;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) total_pos += sm.scratch[w];
-  int CH = PAGE;
-  while (CH > 8 && (total_pos + CH - 1) / CH < ncta) CH >>= 1;
-  // ---- 2. exclusive scan of per-row item counts
-  const int items = (np + CH - 1) / CH;
-  int inc = items;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  __syncthreads();  // scratch reuse
-  if (lane == 31) sm.scratch[warp] = inc;
-  __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < warp; ++w) woff += sm.scratch[w];
-  sm.pre[tid + 1] = woff + inc;  // tid < 256 = MAX_B
-  if (tid == 0) sm.pre[0] = 0;
-  __syncthreads();
-  const int T = sm.pre[n_rows];
-  const int per = (T + ncta - 1) / ncta;
-  const int i0 = cta * per, i1 = min(T, i0 + per);
-  if (i0 >= i1) return;
-  // ---- 3. first row whose items intersect [i0, i1)
-  int lo = 0, hi = n_rows - 1;
-  while (lo < hi) {  // largest r with pre[r] <= i0
-    const int mid = (lo + hi + 1) >> 1;
-    if (sm.pre[mid] <= i0) lo = mid; else hi = mid - 1;
-  }
-  for (int r = lo; r < n_rows && sm.pre[r] < i1; ++r) {
-    const int a0 = max(i0, sm.pre[r]), a1 = min(i1, sm.pre[r + 1]);
-    if (a0 >= a1) continue;  // rows with zero items cannot occur (np >= 1), kept for safety
-    const int npos = ld_cg_i(c.row_pos + r) + 1;
-    const int pbeg = (a0 - sm.pre[r]) * CH, pend = min(npos, (a1 - sm.pre[r]) * CH);
+  if (pr) pr->mark();
+  for (int e = 0; e < 2; ++e) {
+    const int4 ds = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
+    const int r = ds.x;
+    if (r < 0) break;
+    const int pbeg = ds.y, pend = ds.z, j = ds.w >> 16, count = ds.w & 0xFFFF;
     const int slot = ld_cg_i(c.row_slot + r);
-    const int first_cta = sm.pre[r] / per, last_cta = (sm.pre[r + 1] - 1) / per;
-    const int count = last_cta - first_cta + 1;
     float qa[8], qb[8];
     {
       const float* qr = c.q + (size_t)r * D;
@@ -449,12 +522,14 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
       qa[0] = x0.x; qa[1] = x0.y; qa[2] = x0.z; qa[3] = x0.w; qa[4] = x1.x; qa[5] = x1.y; qa[6] = x1.z; qa[7] = x1.w;
       qb[0] = y0.x; qb[1] = y0.y; qb[2] = y0.z; qb[3] = y0.w; qb[4] = y1.x; qb[5] = y1.y; qb[6] = y1.z; qb[7] = y1.w;
     }
+    if (pr) pr->mark();
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, accA[8], accB[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
-    if (pend - pbeg > 32) attn_segment<4>(c, layer, slot, pbeg, pend, qa, qb, m, l, accA, accB);
+    if (pend - pbeg > 16) attn_segment<4>(c, layer, slot, pbeg, pend, qa, qb, m, l, accA, accB);
     else attn_segment<1>(c, layer, slot, pbeg, pend, qa, qb, m, l, accA, accB);
-    __syncthreads();  // previous segment's merge readers are done with sm.m/l/acc
+    if (pr) pr->mark();
+    __syncthreads();  // previous entry's merge readers are done with sm.m/l/acc
     if ((lane & 3) == 0) {
       sm.m[warp][lane >> 2] = m[0]; sm.l[warp][lane >> 2] = l[0];
       sm.m[warp][8 + (lane >> 2)] = m[1]; sm.l[warp][8 + (lane >> 2)] = l[1];
@@ -462,31 +537,47 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sm.acc[warp][lane * 8 + i] = accA[i]; sm.acc[warp][256 + lane * 8 + i] = accB[i]; }
     __syncthreads();
-    attn_merge_write(c, sm, r, r + cta, count);
+    attn_merge_write(c, sm, r, cta, count);
+    if (pr) pr->mark();
     if (count > 1) {
-      __threadfence();
       __syncthreads();
-      if (tid == 0) sm.scratch[NW] = (atomicAdd(c.seg_cnt + r, 1) == count - 1);
+      if (tid == 0) {
+        // release our partial, acquire the others' (acq_rel RMW at gpu scope)
+        int old;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(c.seg_cnt + r) : "memory");
+        sm.scratch[NW] = (old == count - 1);
+      }
       __syncthreads();
-      if (sm.scratch[NW]) {  // last CTA of this sequence: merge all partials
-        __threadfence();
-        const float* pbase = c.part + (size_t)(r + first_cta) * PART_STRIDE;
+      if (pr) pr->mark();
+      if (sm.scratch[NW]) {  // last CTA of this sequence: merge all partials (count <= 16)
+        const float* pbase = c.part + (size_t)(cta - j) * PART_STRIDE;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int d = tid + 256 * k, hd = d >> 5;
-          float mm = -INFINITY;
-          for (int s = 0; s < count; ++s) mm = fmaxf(mm, ld_cg_f(pbase + (size_t)s * PART_STRIDE + hd));
-          float ll = 0.f, aa = 0.f;
-          for (int s = 0; s < count; ++s) {
+          float mv[16], lv[16], av[16];
+#pragma unroll
+          for (int s = 0; s < 16; ++s) {  // every load in flight at once
+            const bool ok = s < count;
             const float* ps = pbase + (size_t)s * PART_STRIDE;
-            const float sc = exp2f(ld_cg_f(ps + hd) - mm);
-            ll += ld_cg_f(ps + NH + hd) * sc;
-            aa += ld_cg_f(ps + 2 * NH + d) * sc;
+            mv[s] = ok ? ld_cg_f(ps + hd) : -INFINITY;
+            lv[s] = ok ? ld_cg_f(ps + NH + hd) : 0.f;
+            av[s] = ok ? ld_cg_f(ps + 2 * NH + d) : 0.f;
+          }
+          float mm = -INFINITY;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) mm = fmaxf(mm, mv[s]);
+          float ll = 0.f, aa = 0.f;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) {  // fixed order: deterministic
+            const float sc = exp2f(mv[s] - mm);
+            ll += lv[s] * sc;
+            aa += av[s] * sc;
           }
           c.attn[(size_t)r * D + d] = __float2bfloat16_rn(aa / ll);
         }
         if (tid == 0) c.seg_cnt[r] = 0;
       }
+      if (pr) pr->mark();
     }
   }
 }
@@ -812,6 +903,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     c.active[p] = slot;
     c.row_slot[p] = slot;
     c.row_pos[p] = pos;
+    c.row_kvoff[p] = ((long long)c.page_table[slot * c.max_pages + (pos >> 6)] * PAGE + (pos & (PAGE - 1))) * D;
     c.seq_len[slot] = pos + 1;
     kvpos = (unsigned long long)(pos + 1);
   }
@@ -821,6 +913,53 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     *c.n_rows = total;
     *c.step = ld_cg_i(c.step) + 1;
     if (total > 0) { atomicAdd(c.stats + 1, 1ull); atomicAdd(c.stats + 2, (unsigned long long)total); }
+  }
+  // ---- split-KV work assignment for the next step's attention (valid for all layers)
+  int* np_s = smem_i + 16;        // [MAX_B] positions per new row
+  if (keep) np_s[woff + inc - 1] = (int)kvpos;
+  const int ncta = c.attn_ctas;
+  int4* desc = reinterpret_cast<int4*>(c.attn_desc);
+  for (int i = tid; i < 2 * ncta; i += NT) desc[i] = make_int4(-1, 0, 0, 0);
+  __syncthreads();
+  const int n2 = total;
+  if (n2 == 0) return;
+  if (n2 > ncta) {  // more rows than CTAs: whole rows, round-robin (n2 <= MAX_B < 2 * ncta)
+    if (tid < n2) desc[(tid % ncta) * 2 + tid / ncta] = make_int4(tid, 0, np_s[tid], 1);
+    return;
+  }
+  // Np
+  int v = (tid < n2) ? np_s[tid] : 0, tot = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  __syncthreads();
+  if (lane == 0) smem_i[warp] = tot;
+  __syncthreads();
+  long long Np = 0;
+  for (int w = 0; w < NW; ++w) Np += smem_i[w];
+  // CTAs per row: 1 + share of the spare CTAs, capped by 16 partials and by the number of 8-position items
+  int k = 0;
+  if (tid < n2) {
+    k = 1 + (int)(((long long)(ncta - n2) * v) / Np);
+    k = min(k, 16);
+    k = min(k, (v + 7) >> 3);
+  }
+  int kin = k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int x = __shfl_up_sync(0xffffffffu, kin, o);
+    if (lane >= o) kin += x;
+  }
+  __syncthreads();
+  if (lane == 31) smem_i[warp] = kin;
+  __syncthreads();
+  int koff = 0;
+  for (int w = 0; w < warp; ++w) koff += smem_i[w];
+  const int c0 = koff + kin - k;  // first CTA of this row
+  if (tid < n2) {
+    const int q = (((v + k - 1) / k) + 7) & ~7;  // positions per CTA, multiple of 8
+    const int count = (v + q - 1) / q;
+    for (int jj = 0; jj < count; ++jj)
+      desc[(c0 + jj) * 2] = make_int4(tid, jj * q, min(v, (jj + 1) * q), (jj << 16) | count);
   }
 }
 

@@ -139,13 +139,21 @@ int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, int32_t widt
                      int32_t top_k, float top_p, float temperature, float repetition_penalty, uint64_t seed,
                      int32_t step, int32_t* tok_out, int32_t* greedy_out, void* stream);
 
+/* Measurement hook: during persistent-kernel iteration `step` of the next t2s_decode, thread 0 of every CTA
+ * records its SM clock when it arrives at / is released from each grid barrier:
+ * buf[cta][slots][2] (device, int64); probe[cta][2][32] (device, int64, optional) receives intra-phase marks
+ * of layer 1's QKV and attention phases.  Set before t2s_prefill; NULL clears. */
+int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots, long long* probe);
+
+/* Measurement hook: latency of n_barriers back-to-back grid barriers of the persistent kernel. */
+int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* ms_out, void* stream);
+
 enum {
-  T2S_OPT_DECODE_MODE = 0,   /* 0: one kernel per phase, CUDA-graph replay; 1: persistent cooperative kernel */
+  T2S_OPT_DECODE_MODE = 0,   /* 0: one kernel per phase, CUDA-graph replay; 1: persistent cooperative kernel;
+                                2: one kernel per phase, plain stream launches (profiling aid) */
   T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */
   T2S_OPT_NUM_CTAS = 2,      /* persistent grid size (0 = one CTA per SM) */
-  T2S_OPT_CHECK_STEPS = 3,   /* graph mode: host checks the active count every this many steps */
-  T2S_OPT_DETERMINISTIC = 4  /* 1 (default): no floating-point atomics, results reproducible bit for bit;
-                                0: FFN2 split-K partials are combined with fp32 atomics (4x more units) */
+  T2S_OPT_CHECK_STEPS = 3    /* graph mode: host checks the active count every this many steps */
 };
 int t2s_set_option(t2s_engine* e, int32_t option, int64_t value);
 

@@ -11,7 +11,7 @@ ids = [t.cuda() for t in ids]; bert = [t.cuda() for t in bert]
 n = g["logits"].shape[0]
 for det in (1, 0):
   for mode in (0, 1):
-    eng.set_option(_lib.OPT_DETERMINISTIC, det); eng.set_option(_lib.OPT_DECODE_MODE, mode)
+    eng.set_option(_lib.OPT_DECODE_MODE, mode)
     r = eng.infer(ids, bert, None, top_k=1, early_stop_num=20, eos_suppress_steps=11, capture_logits=n)
     got = r.logits.cpu().numpy()
     d = [float(np.abs(got[s,0,:1024]-g["logits"][s,0,:1024]).max()) for s in range(n)]
