@@ -92,6 +92,8 @@ struct t2s_engine {
   long long* probe = nullptr;
   int tl_step = 0, tl_slots = 0;
   int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
+  bool tc_ok = false;
+  DevBuf xf, xb;  // tcgen05 prefill path: LayerNorm'ed rows (fp32 residual + bf16 GEMM operand)
   // graph cache (decode_mode 0)
   cudaGraphExec_t graph_exec = nullptr;
   Ctx graph_ctx{};
@@ -169,7 +171,8 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   cudaFuncSetAttribute(k_phase<PH_PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
   cudaFuncSetAttribute(k_bert_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
   cudaFuncSetAttribute(k_decode_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-  gemm_tc_init();
+  e->tc_ok = gemm_tc_init();
+  e->prefill_gemm = e->tc_ok ? 1 : 0;  // tcgen05/TMEM + TMA GEMMs for prefill unless the driver entry point is missing
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     t2s_destroy(e);
@@ -188,7 +191,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
-                    &e->bert_rows, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
+                    &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
   for (DevBuf* b : bufs) b->release();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -303,7 +306,10 @@ extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
     case T2S_OPT_DECODE_MODE: if (v < 0 || v > 2) return fail("decode mode must be 0, 1 or 2"); e->decode_mode = (int)v; break;
-    case T2S_OPT_PREFILL_GEMM: if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1"); e->prefill_gemm = (int)v; break;
+    case T2S_OPT_PREFILL_GEMM:
+      if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
+      if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
+      e->prefill_gemm = (int)v; break;
     case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
@@ -410,6 +416,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   rc |= e->gen.ensure((size_t)B * rq->max_steps * 4);
   rc |= e->sampled.ensure((size_t)B * rq->max_steps * 4);
   rc |= e->bert_rows.ensure((size_t)n_text * BERT * 2);
+  if (e->prefill_gemm) { rc |= e->xf.ensure((size_t)T * D * 4); rc |= e->xb.ensure((size_t)T * D * 2); }
   if (rc) return 1;
   // pack the int arrays into one upload
   std::vector<int> hi(n_ints, 0);
@@ -529,14 +536,52 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
     k_bert_rows<bf16><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
   k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
   e->launches += 4;
+  if (e->prefill_gemm) {
+    // tcgen05/TMEM + TMA GEMMs (gemm_tc.cuh); LayerNorm rows are materialised once per sub-layer
+    float* xf = e->xf.as<float>();
+    bf16* xb = e->xb.as<bf16>();
+    const int ln_blocks = (T + 7) / 8;
+    bool ok = true;
+    for (int l = 0; l < cp.n_layer && ok; ++l) {
+      const float* vl = cp.wvec + (size_t)l * LV;
+      const bf16* wr = e->wrow.as<bf16>() + (size_t)l * LW;
+      const float* resid;
+      if (l == 0) {
+        k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.x0, nullptr, nullptr, nullptr, xb, T, 0);
+        resid = cp.x0;
+      } else {
+        const float* vp = cp.wvec + (size_t)(l - 1) * LV;
+        k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.y2, vp + VO_G2, vp + VO_BE2, xf, xb, T, 1);
+        resid = xf;
+      }
+      TcEpilogue ep{};
+      ep.error_flag = cp.abort_flag;
+      ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
+      ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
+      ok = ok && launch_gemm_tc(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
+      k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+      ep = TcEpilogue{};
+      ep.error_flag = cp.abort_flag;
+      ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;
+      ok = ok && launch_gemm_tc(cp.attn, wr + OFF_WO, T, D, D, ep, s);
+      k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.y1, vl + VO_G1, vl + VO_BE1, xf, xb, T, 1);
+      ep.mode = EPI_RELU; ep.bias = vl + VO_B1; ep.resid = nullptr; ep.out_f32 = nullptr; ep.out_b16 = cp.h;
+      ok = ok && launch_gemm_tc(xb, wr + OFF_W1, T, FF, D, ep, s);
+      ep.mode = EPI_RESID; ep.bias = vl + VO_B2; ep.resid = xf; ep.out_f32 = cp.y2; ep.out_b16 = nullptr;
+      ok = ok && launch_gemm_tc(cp.h, wr + OFF_W2, T, D, FF, ep, s);
+      e->launches += 7;
+    }
+    if (!ok) return fail("t2s_prefill: cuTensorMapEncodeTiled failed");
+  } else {
   for (int l = 0; l < cp.n_layer; ++l) {
-    launch_phase<PH_QKV>(e, cp, l, g, s);
-    k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
-    e->launches++;
-    launch_phase<PH_OPROJ>(e, cp, l, g, s);
-    launch_phase<PH_FFN1>(e, cp, l, g, s);
-    launch_phase<PH_FFN2>(e, cp, l, g, s);
-  }
+      launch_phase<PH_QKV>(e, cp, l, g, s);
+      k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+      e->launches++;
+      launch_phase<PH_OPROJ>(e, cp, l, g, s);
+      launch_phase<PH_FFN1>(e, cp, l, g, s);
+      launch_phase<PH_FFN2>(e, cp, l, g, s);
+    }
+}
   launch_phase<PH_HEAD>(e, cp, 0, g, s);           // rows = n_active = B, gathered through head_rows
   launch_phase<PH_SAMPLE>(e, e->cd, 0, std::min(B, g), s);  // step 0 sample; writes the decode-side x0
   launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);

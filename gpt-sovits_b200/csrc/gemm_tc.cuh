@@ -1,5 +1,287 @@
-// gemm_tc.cuh — tcgen05/TMEM + TMA GEMM for the prefill projections (placeholder until the kernel lands).
+// gemm_tc.cuh — prefill projections on the 5th-generation tensor cores.
+//
+//   C[M, N] = A[M, K] (bf16, row-major)  x  W[N, K]^T (bf16, row-major)   with a fused epilogue
+//
+// One CTA computes a 128 x 128 output tile.  Warp roles (256 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D boxes (128 rows x 64 k) of A and W into a 4-stage
+//            shared-memory ring, 128-byte swizzle, completion on mbarriers (expect_tx)
+//   warp 1   MMA issuer: ONE elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16)
+//            from shared-memory descriptors; the accumulator lives in TMEM (128 lanes x 128 fp32 columns);
+//            tcgen05.commit releases ring slots and finally signals the epilogue
+//   warp 2   TMEM allocation / deallocation
+//   warps 4-7 epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> registers -> bias / ReLU / residual ->
+//            global (fp32 or bf16), or the KV-cache scatter for the QKV projection
+//
+// Replaces the F.linear calls of T2SBlock.process_prompt (t2s_model.py:142,162) and T2SMLP (:81-84).
+// Descriptor encodings follow the PTX ISA tables for tcgen05 shared-memory / instruction descriptors
+// (K-major operands, SWIZZLE_128B: 8-row x 128-byte atoms, stride-byte-offset 1024).
 #pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
 namespace t2s {
-static inline void gemm_tc_init() {}
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 256;
+constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;  // 32 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_RELU = 2 };
+
+struct TcEpilogue {
+  int mode;
+  const float* bias;     // [N]
+  const float* resid;    // EPI_RESID: [M, N] fp32
+  float* out_f32;        // EPI_RESID: [M, N]; EPI_QKV: q [M, 512]
+  bf16* out_b16;         // EPI_RELU: [M, N]
+  bf16* kpool;           // EPI_QKV
+  bf16* vpool;
+  const long long* kvoff;  // [M] element offset of each row's cache position
+  size_t layer_off;        // layer * kv_layer_stride
+  int* error_flag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a lost arrival becomes an error flag instead of a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  for (unsigned spins = 0; spins < 400000000u; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  atomicExch(error_flag, 1);
+  return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+          TcEpilogue ep) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int nkb = K / TC_BK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        if (!mbar_wait(empty0 + 8 * s, ph ^ 1, ep.error_flag)) break;
+        const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES), sb = sa + TC_BM * TC_BK * 2;
+        mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
+        tma_load_2d(sa, &map_a, kb * TC_BK, m0, full0 + 8 * s);
+        tma_load_2d(sb, &map_w, kb * TC_BK, n0, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        if (!mbar_wait(full0 + 8 * s, ph, ep.error_flag)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES), sb = sa + TC_BM * TC_BK * 2;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)  // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the address field
+          umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(empty0 + 8 * s);  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(done_bar);  // accumulator complete
+    }
+  } else if (warp >= 4) {  // ===== epilogue =====
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(done_bar, 0, ep.error_flag);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + wq * 32 + lane;
+    const bool row_ok = row < M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    long long kvo = 0;
+    if (ep.mode == EPI_QKV && row_ok && n0 >= D) kvo = ep.kvoff[row];
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+      const int f0 = n0 + c0;
+      float x[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + ep.bias[f0 + j];
+      if (ep.mode == EPI_QKV) {
+        if (f0 < D) {
+          float4* o = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * D + f0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_float4(x[4 * j] * QSCALE, x[4 * j + 1] * QSCALE, x[4 * j + 2] * QSCALE, x[4 * j + 3] * QSCALE);
+        } else {
+          bf16* base = (f0 < 2 * D ? ep.kpool + (f0 - D) : ep.vpool + (f0 - 2 * D)) + ep.layer_off + (size_t)kvo;
+          uint4* o = reinterpret_cast<uint4*>(base);
+          o[0] = make_uint4(pack_bf2(x[0], x[1]), pack_bf2(x[2], x[3]), pack_bf2(x[4], x[5]), pack_bf2(x[6], x[7]));
+          o[1] = make_uint4(pack_bf2(x[8], x[9]), pack_bf2(x[10], x[11]), pack_bf2(x[12], x[13]), pack_bf2(x[14], x[15]));
+        }
+      } else if (ep.mode == EPI_RESID) {
+        const float4* r4 = reinterpret_cast<const float4*>(ep.resid + (size_t)row * N + f0);
+        float4* o = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * N + f0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 rr = r4[j];
+          o[j] = make_float4(rr.x + x[4 * j], rr.y + x[4 * j + 1], rr.z + x[4 * j + 2], rr.w + x[4 * j + 3]);
+        }
+      } else {
+        uint4* o = reinterpret_cast<uint4*>(ep.out_b16 + (size_t)row * N + f0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+        o[0] = make_uint4(pack_bf2(x[0], x[1]), pack_bf2(x[2], x[3]), pack_bf2(x[4], x[5]), pack_bf2(x[6], x[7]));
+        o[1] = make_uint4(pack_bf2(x[8], x[9]), pack_bf2(x[10], x[11]), pack_bf2(x[12], x[13]), pack_bf2(x[14], x[15]));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+  }
+}
+
+// LayerNorm (or plain copy) of fp32 rows -> fp32 + bf16 copies, one warp per row: feeds the GEMM's A operand
+// and its residual (F.layer_norm, t2s_model.py:165-173).
+__global__ void k_ln_rows(const float* __restrict__ in, const float* __restrict__ g, const float* __restrict__ b,
+                          float* __restrict__ out_f32, bf16* __restrict__ out_b16, int n_rows, int apply_ln) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float* src = in + (size_t)row * D;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(src + lane * 4 + 128 * j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+  if (apply_ln) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float d = v[j] - mean; sq += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / D) + LN_EPS);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 gg = *reinterpret_cast<const float4*>(g + lane * 4 + 128 * j);
+      const float4 bb = *reinterpret_cast<const float4*>(b + lane * 4 + 128 * j);
+      v[4 * j] = (v[4 * j] - mean) * rstd * gg.x + bb.x;
+      v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * gg.y + bb.y;
+      v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * gg.z + bb.z;
+      v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * gg.w + bb.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * D + lane * 4 + 128 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    uint2 p = make_uint2(pack_bf2(v[4 * j], v[4 * j + 1]), pack_bf2(v[4 * j + 2], v[4 * j + 3]));
+    *reinterpret_cast<uint2*>(out_b16 + (size_t)row * D + lane * 4 + 128 * j) = p;
+  }
+}
+
+// ---- host side: TMA tensor maps through the driver entry point (no libcuda link dependency) -------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_tmap_encode = nullptr;
+
+static inline bool gemm_tc_init() {
+  if (g_tmap_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn)
+    return false;
+  g_tmap_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  return true;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = 128 rows x 64 cols, 128-byte swizzle, OOB rows read as zero
+static inline bool make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  return g_tmap_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// C = A[M,K] * W[N,K]^T with epilogue `ep`; returns false when the tensor maps cannot be built
+static inline bool launch_gemm_tc(const bf16* A, const bf16* W, int M, int N, int K, const TcEpilogue& ep, cudaStream_t s) {
+  CUtensorMap ma, mw;
+  if (!make_tmap_bf16(&ma, A, (uint64_t)M, (uint64_t)K) || !make_tmap_bf16(&mw, W, (uint64_t)N, (uint64_t)K)) return false;
+  dim3 grid((M + TC_BM - 1) / TC_BM, N / TC_BN);
+  k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mw, M, N, K, ep);
+  return true;
+}
+
 }  // namespace t2s

@@ -15,11 +15,12 @@ ap.add_argument("--lo", type=int, default=60)
 ap.add_argument("--hi", type=int, default=120)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--det", type=int, default=1)
+ap.add_argument("--tc", type=int, default=0)
 ap.add_argument("--barrier-bench", action="store_true")
 a = ap.parse_args()
 sd = synthetic.make_state_dict(seed=0, eos_scale=0.0)
 eng = gsb.T2SEngine(synthetic.S1V2_CONFIG); eng.load_state_dict(sd, pe=synthetic.sine_pe())
-eng.set_option(_lib.OPT_DECODE_MODE, a.mode);
+eng.set_option(_lib.OPT_DECODE_MODE, a.mode); eng.set_option(_lib.OPT_PREFILL_GEMM, a.tc);
 if a.barrier_bench:
     for ncta in (148, 74, 37):
         for n in (1000, 10000):
@@ -34,6 +35,6 @@ for rep in range(a.reps):
                   early_stop_num=a.steps, eos_suppress_steps=1, seed=1 + rep)
     st = r.stats
     by = st["decode_steps"] * st["weight_bytes_per_step"] + st["kv_bytes_per_position"] * (st["decode_kv_positions"] + st["decode_tokens"])
-    print(f"mode {a.mode} det {a.det} B={a.batch}: prefill {st['prefill_ms']:.2f} ms ({int(st['prefill_rows'])} rows), decode {st['decode_ms']:.2f} ms / "
+    print(f"mode {a.mode} tc {a.tc} B={a.batch}: prefill {st['prefill_ms']:.2f} ms ({int(st['prefill_rows'])} rows), decode {st['decode_ms']:.2f} ms / "
           f"{int(st['decode_steps'])} steps = {1000*st['decode_ms']/max(st['decode_steps'],1):.1f} us/step, "
           f"{by/st['decode_ms']/1e6:.0f} GB/s algorithmic, mean KV {st['decode_kv_positions']/max(st['decode_tokens'],1):.0f}")
