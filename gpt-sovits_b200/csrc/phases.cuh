@@ -438,6 +438,72 @@ __device__ __forceinline__ void attn_merge_write(const Ctx& c, AttnSmem& sm, int
   }
 }
 
+// K/V rows of U consecutive positions starting at p0 (same page: p0 is a multiple of U <= 4)
+template <int U>
+__device__ __forceinline__ void attn_load(const bf16* kbase, const bf16* vbase, const int* pt, int p0, int pend, int lane,
+                                          uint4 (&ka)[U], uint4 (&kb)[U], uint4 (&va)[U], uint4 (&vb)[U]) {
+  const int page = pt[p0 >> 6];
+  const size_t rowoff = ((size_t)page * PAGE + (p0 & (PAGE - 1))) * D;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (p0 + u < pend) {
+      const bf16* kr = kbase + rowoff + (size_t)u * D;
+      const bf16* vr = vbase + rowoff + (size_t)u * D;
+      ka[u] = ld_cg16(kr + lane * 8);
+      kb[u] = ld_cg16(kr + 256 + lane * 8);
+      va[u] = ld_cg16(vr + lane * 8);
+      vb[u] = ld_cg16(vr + 256 + lane * 8);
+    } else {
+      ka[u] = kb[u] = va[u] = vb[u] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void attn_accumulate(int p0, int pend, const uint4 (&ka)[U], const uint4 (&kb)[U],
+                                                const uint4 (&va)[U], const uint4 (&vb)[U], const float (&qa)[8],
+                                                const float (&qb)[8], float (&m)[2], float (&l)[2], float (&accA)[8],
+                                                float (&accB)[8]) {
+  float sA[U], sB[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float a = qa[0] * bf_lo(ka[u].x) + qa[1] * bf_hi(ka[u].x) + qa[2] * bf_lo(ka[u].y) + qa[3] * bf_hi(ka[u].y) +
+              qa[4] * bf_lo(ka[u].z) + qa[5] * bf_hi(ka[u].z) + qa[6] * bf_lo(ka[u].w) + qa[7] * bf_hi(ka[u].w);
+    float b = qb[0] * bf_lo(kb[u].x) + qb[1] * bf_hi(kb[u].x) + qb[2] * bf_lo(kb[u].y) + qb[3] * bf_hi(kb[u].y) +
+              qb[4] * bf_lo(kb[u].z) + qb[5] * bf_hi(kb[u].z) + qb[6] * bf_lo(kb[u].w) + qb[7] * bf_hi(kb[u].w);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    const bool ok = (p0 + u < pend);
+    sA[u] = ok ? a : -INFINITY;
+    sB[u] = ok ? b : -INFINITY;
+  }
+  float mA = m[0], mB = m[1];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { mA = fmaxf(mA, sA[u]); mB = fmaxf(mB, sB[u]); }
+  const float cA = exp2f(m[0] - mA), cB = exp2f(m[1] - mB);  // position p0 is valid, so mA/mB are finite
+  m[0] = mA; m[1] = mB;
+  l[0] *= cA; l[1] *= cB;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { accA[i] *= cA; accB[i] *= cB; }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float pA = exp2f(sA[u] - mA), pB = exp2f(sB[u] - mB);
+    l[0] += pA; l[1] += pB;
+    accA[0] += pA * bf_lo(va[u].x); accA[1] += pA * bf_hi(va[u].x);
+    accA[2] += pA * bf_lo(va[u].y); accA[3] += pA * bf_hi(va[u].y);
+    accA[4] += pA * bf_lo(va[u].z); accA[5] += pA * bf_hi(va[u].z);
+    accA[6] += pA * bf_lo(va[u].w); accA[7] += pA * bf_hi(va[u].w);
+    accB[0] += pB * bf_lo(vb[u].x); accB[1] += pB * bf_hi(vb[u].x);
+    accB[2] += pB * bf_lo(vb[u].y); accB[3] += pB * bf_hi(vb[u].y);
+    accB[4] += pB * bf_lo(vb[u].z); accB[5] += pB * bf_hi(vb[u].z);
+    accB[6] += pB * bf_lo(vb[u].w); accB[7] += pB * bf_hi(vb[u].w);
+  }
+}
+
+// One warp walks positions pbeg + U*warp, + U*NW, ... with the NEXT group's loads in flight while the current
+// group is reduced (two register buffers, loop unrolled by two so the buffers are never copied).
 template <int U>
 __device__ __forceinline__ void attn_segment(const Ctx& c, int layer, int slot, int pbeg, int pend,
                                              const float (&qa)[8], const float (&qb)[8],
@@ -446,59 +512,21 @@ __device__ __forceinline__ void attn_segment(const Ctx& c, int layer, int slot, 
   const bf16* kbase = c.kpool + (size_t)layer * c.kv_layer_stride;
   const bf16* vbase = c.vpool + (size_t)layer * c.kv_layer_stride;
   const int* pt = c.page_table + slot * c.max_pages;
-  for (int p0 = pbeg + U * warp; p0 < pend; p0 += U * NW) {
-    const int page = pt[p0 >> 6];
-    const size_t rowoff = ((size_t)page * PAGE + (p0 & (PAGE - 1))) * D;
-    uint4 ka[U], kb[U], va[U], vb[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (p0 + u < pend) {
-        const bf16* kr = kbase + rowoff + (size_t)u * D;
-        const bf16* vr = vbase + rowoff + (size_t)u * D;
-        ka[u] = ld_cg16(kr + lane * 8);
-        kb[u] = ld_cg16(kr + 256 + lane * 8);
-        va[u] = ld_cg16(vr + lane * 8);
-        vb[u] = ld_cg16(vr + 256 + lane * 8);
-      } else {
-        ka[u] = kb[u] = va[u] = vb[u] = make_uint4(0, 0, 0, 0);
-      }
-    }
-    float sA[U], sB[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float a = qa[0] * bf_lo(ka[u].x) + qa[1] * bf_hi(ka[u].x) + qa[2] * bf_lo(ka[u].y) + qa[3] * bf_hi(ka[u].y) +
-                qa[4] * bf_lo(ka[u].z) + qa[5] * bf_hi(ka[u].z) + qa[6] * bf_lo(ka[u].w) + qa[7] * bf_hi(ka[u].w);
-      float b = qb[0] * bf_lo(kb[u].x) + qb[1] * bf_hi(kb[u].x) + qb[2] * bf_lo(kb[u].y) + qb[3] * bf_hi(kb[u].y) +
-                qb[4] * bf_lo(kb[u].z) + qb[5] * bf_hi(kb[u].z) + qb[6] * bf_lo(kb[u].w) + qb[7] * bf_hi(kb[u].w);
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      b += __shfl_xor_sync(0xffffffffu, b, 1);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      b += __shfl_xor_sync(0xffffffffu, b, 2);
-      const bool ok = (p0 + u < pend);
-      sA[u] = ok ? a : -INFINITY;
-      sB[u] = ok ? b : -INFINITY;
-    }
-    float mA = m[0], mB = m[1];
-#pragma unroll
-    for (int u = 0; u < U; ++u) { mA = fmaxf(mA, sA[u]); mB = fmaxf(mB, sB[u]); }
-    const float cA = exp2f(m[0] - mA), cB = exp2f(m[1] - mB);  // position p0 is valid, so mA/mB are finite
-    m[0] = mA; m[1] = mB;
-    l[0] *= cA; l[1] *= cB;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { accA[i] *= cA; accB[i] *= cB; }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float pA = exp2f(sA[u] - mA), pB = exp2f(sB[u] - mB);
-      l[0] += pA; l[1] += pB;
-      accA[0] += pA * bf_lo(va[u].x); accA[1] += pA * bf_hi(va[u].x);
-      accA[2] += pA * bf_lo(va[u].y); accA[3] += pA * bf_hi(va[u].y);
-      accA[4] += pA * bf_lo(va[u].z); accA[5] += pA * bf_hi(va[u].z);
-      accA[6] += pA * bf_lo(va[u].w); accA[7] += pA * bf_hi(va[u].w);
-      accB[0] += pB * bf_lo(vb[u].x); accB[1] += pB * bf_hi(vb[u].x);
-      accB[2] += pB * bf_lo(vb[u].y); accB[3] += pB * bf_hi(vb[u].y);
-      accB[4] += pB * bf_lo(vb[u].z); accB[5] += pB * bf_hi(vb[u].z);
-      accB[6] += pB * bf_lo(vb[u].w); accB[7] += pB * bf_hi(vb[u].w);
-    }
+  constexpr int STEP = U * NW;
+  int p0 = pbeg + U * warp;
+  if (p0 >= pend) return;
+  uint4 ka0[U], kb0[U], va0[U], vb0[U], ka1[U], kb1[U], va1[U], vb1[U];
+  attn_load<U>(kbase, vbase, pt, p0, pend, lane, ka0, kb0, va0, vb0);
+  for (;;) {
+    const int p1 = p0 + STEP;
+    if (p1 < pend) attn_load<U>(kbase, vbase, pt, p1, pend, lane, ka1, kb1, va1, vb1);
+    attn_accumulate<U>(p0, pend, ka0, kb0, va0, vb0, qa, qb, m, l, accA, accB);
+    if (p1 >= pend) break;
+    const int p2 = p1 + STEP;
+    if (p2 < pend) attn_load<U>(kbase, vbase, pt, p2, pend, lane, ka0, kb0, va0, vb0);
+    attn_accumulate<U>(p1, pend, ka1, kb1, va1, vb1, qa, qb, m, l, accA, accB);
+    if (p2 >= pend) break;
+    p0 = p2;
   }
 }
 

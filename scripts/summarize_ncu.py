@@ -1,0 +1,51 @@
+"""Turns gpurun_out ncu artefacts into the tracked summaries under profiles/."""
+import collections, csv, io, subprocess, sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = []
+# (a) launch list of the bench command
+fn = os.path.join(ROOT, "gpurun_out", "launches_bench.csv")
+if os.path.exists(fn):
+    lines = [l for l in open(fn) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    agg = collections.OrderedDict()
+    for r in rows:
+        n = r["Kernel Name"].split("(")[0].replace("void ", "")
+        agg.setdefault(n, []).append(float(r["Metric Value"].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    out.append(f"## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none) of `python bench.py --steps 1 --warmup 1 --no-cpu`\n")
+    out.append(f"{len(rows)} launches of this library's kernels (weight-packing kernels at engine creation excluded by the kernel-name filter); "
+               f"per-launch times are cold-cache and serialised: compare SHARES.\n")
+    out.append("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
+    for k, v in agg.items():
+        out.append(f"| `{k}` | {len(v)} | {sum(v)/1e6:.3f} | {100*sum(v)/tot:.1f}% |")
+    out.append("")
+    with open(os.path.join(ROOT, "profiles", f"{tag}_launches_bench.csv"), "w") as f:
+        f.write("kernel,launches,total_ns\n")
+        for k, v in agg.items():
+            f.write(f"{k},{len(v)},{sum(v):.0f}\n")
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
+        "launch__shared_mem_per_block_dynamic"]
+for rep, title in (("prof_decode_b32", "k_decode_persistent, B=32, 60 decode steps (mean KV ~ 280) — `ncu --set full --clock-control none`"),
+                   ("prof_prefill_b32", "prefill kernels (k_gemm_tc / k_prefill_attn), B=32 (7755 rows) — `ncu --set full`")):
+    path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
+    if not os.path.exists(path):
+        continue
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out.append(f"## {title}\n")
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0]
+        out.append(f"### `{name}` (id {r[0]})\n\n| metric | value | unit |\n|---|---:|---|")
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                out.append(f"| {w} | {r[i]} | {units[i]} |")
+        out.append("")
+open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out)[:6000])
