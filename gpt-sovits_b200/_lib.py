@@ -115,7 +115,7 @@ def load() -> C.CDLL:
     lib.t2s_sampler_test.argtypes = [vp, vp, i32, i32, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_uint64, i32,
                                      vp, vp, vp]
     lib.t2s_bench_barrier.argtypes = [vp, i32, i32, C.POINTER(C.c_float), vp]
-    lib.t2s_set_timeline.argtypes = [vp, vp, i32, i32, vp]
+    lib.t2s_set_timeline.argtypes = [vp, vp, i32, i32]
     for name in EXPORTS:
         if name not in ("t2s_destroy", "t2s_last_error"):
             getattr(lib, name).restype = i32

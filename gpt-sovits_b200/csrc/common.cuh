@@ -34,7 +34,9 @@ constexpr size_t OFF_W1 = OFF_WO + (size_t)D * D;
 constexpr size_t OFF_W2 = OFF_W1 + (size_t)FF * D;
 constexpr size_t LW = OFF_W2 + (size_t)D * FF;  // 3,145,728
 constexpr int VO_BQKV = 0, VO_BO = 1536, VO_B1 = 2048, VO_B2 = 4096, VO_G1 = 4608, VO_BE1 = 5120,
-              VO_G2 = 5632, VO_BE2 = 6144, LV = 6656;
+              VO_G2 = 5632, VO_BE2 = 6144,
+              // LayerNorm folded into the consumer GEMMs (k_fold_ln): c1 = Wg 1, c0 = W beta + bias
+              VO_C1_QKV = 6656, VO_C0_QKV = 8192, VO_C1_FFN1 = 9728, VO_C0_FFN1 = 11776, LV = 13824;
 
 constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
 
@@ -45,7 +47,9 @@ struct Ctx {
   // model
   const bf16* wmat;       // [n_layer][LW], each matrix in MMA-fragment tile order (see pack.cuh)
   const float* wvec;      // [n_layer][LV]
-  const bf16* whead;      // ar_predict_layer, packed, VT tiles
+  const bf16* whead;      // ar_predict_layer (gamma-folded), packed, VT tiles
+  const float* head_c1;   // [VPAD]
+  const float* head_c0;
   const bf16* wbert;      // bert_proj.weight packed (32 tiles x 64 k-blocks)
   const float* bbert;     // bert_proj.bias
   const bf16* emb_audio;  // [V][D] row-major bf16
@@ -69,11 +73,16 @@ struct Ctx {
   int x0_by_slot;        // layer-0 input indexed by slot (decode) or by row (prefill)
   // activations
   float* x0;
+  bf16* x0b;     // bf16 copy of x0 (GEMM operand)
   float* q;
   bf16* attn;
-  float* y1;
+  float* y1;     // residual sums (pre-LayerNorm), fp32 ...
+  bf16* yb1;     // ... their bf16 copies (next GEMM's operand) ...
+  float2* sp1;   // ... and per-16-feature-tile partial (sum, sum of squares) [rows][32]
   bf16* h;
   float* y2;
+  bf16* yb2;
+  float2* sp2;
   float2* stat2;
   float* logits;  // [MAX_B][VPAD]
   // decode attention split-KV scratch
@@ -105,7 +114,6 @@ struct Ctx {
   unsigned long long* stats;  // [0] kv positions, [1] steps, [2] sequence-steps
   long long* timeline;        // measurement hook: [ncta][tl_slots][2] (arrive, release) SM clocks of one step
   int tl_step, tl_slots;
-  long long* probe;           // measurement hook: [ncta][2][32] intra-phase marks (qkv, attention of layer 1)
 };
 
 // ---- loads / stores ------------------------------------------------------------------------------
@@ -122,6 +130,24 @@ __device__ __forceinline__ uint4 ld_cg16(const void* p) { return __ldcg(reinterp
 __device__ __forceinline__ float4 ld_cg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float ld_cg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ int ld_cg_i(const int* p) { return __ldcg(p); }
+
+// volatile variants: keep their program order, so a batch of independent loads is issued back to back
+// (one L2 round trip) instead of being sunk to their first use by the compiler
+__device__ __forceinline__ uint4 ldv_cg16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldv_cg_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ long long ldv_cg_ll(const long long* p) {
+  long long r;
+  asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
 
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }

@@ -64,13 +64,15 @@ struct t2s_engine {
   int device = 0, num_sms = 0;
   // weights
   DevBuf wmat, wvec, whead, wbert, bbert, emb_audio, emb_text, pe, wrow;  // wrow: row-major bf16 copies for the TMA GEMM
+  DevBuf wrow_g, wrow_head, wrow_head_g, head_c;  // gamma-folded row-major copies (Wqkv, W1 per layer; head) + head c1/c0
+  bool weights_final = false;
   float alpha_audio = 1.f, alpha_text = 1.f;
   std::vector<char> loaded;  // per (tensor, layer)
   // kv pool
   DevBuf kpool, vpool;
   size_t pool_pages = 0;
   // session buffers
-  DevBuf ints, ints2, kvoff, attn_desc, x0_rows, x0_slots, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
+  DevBuf ints, ints2, kvoff, attn_desc, x0_rows, x0_slots, x0b_rows, x0b_slots, yb1, yb2, sp1, sp2, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
   DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx;
   Ctx cp{}, cd{};  // prefill / decode contexts
   bool session = false;
@@ -89,7 +91,6 @@ struct t2s_engine {
   float* logits_rec = nullptr;
   int n_logits_rec = 0;
   long long* timeline = nullptr;
-  long long* probe = nullptr;
   int tl_step = 0, tl_slots = 0;
   int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
   bool tc_ok = false;
@@ -144,6 +145,11 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   rc |= e->emb_text.ensure((size_t)cfg->phoneme_vocab * D * 2);
   rc |= e->pe.ensure((size_t)cfg->pe_len * D * 4);
   rc |= e->wrow.ensure(((size_t)L * LW + (size_t)D * BERT) * 2);
+  rc |= e->wrow_g.ensure((size_t)L * (3 * D + FF) * D * 2);
+  rc |= e->wrow_head.ensure((size_t)VPAD * D * 2);
+  rc |= e->wrow_head_g.ensure((size_t)VPAD * D * 2);
+  rc |= e->head_c.ensure((size_t)2 * VPAD * 4);
+  rc |= e->x0b_slots.ensure((size_t)MAX_B * D * 2);
   rc |= e->logits.ensure((size_t)MAX_B * VPAD * 4);
   rc |= e->part.ensure((size_t)(MAX_B + 1024) * PART_STRIDE * 4);
   rc |= e->seg_cnt.ensure(MAX_B * 4);
@@ -189,6 +195,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
+                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
@@ -270,10 +277,10 @@ extern "C" int t2s_load_tensor(t2s_engine* e, int32_t id, int32_t layer, const v
       break;
     }
     case T2S_W_PE: cvt_f32(e->pe.as<float>(), (size_t)e->cfg.pe_len * D); break;
-    case T2S_W_PREDICT: pack(e->whead.as<bf16>(), V, D, VT); break;
-    case T2S_W_IN_PROJ_W: pack(wl + OFF_WQKV, 3 * D, D, 3 * D / 16); cvt_b16(wr + OFF_WQKV, (size_t)3 * D * D); break;
+    case T2S_W_PREDICT: cvt_b16(e->wrow_head.as<bf16>(), (size_t)V * D); break;  // packed by finalize_weights (LN fold)
+    case T2S_W_IN_PROJ_W: cvt_b16(wr + OFF_WQKV, (size_t)3 * D * D); break;  // packed by finalize_weights
     case T2S_W_OUT_PROJ_W: pack(wl + OFF_WO, D, D, D / 16); cvt_b16(wr + OFF_WO, (size_t)D * D); break;
-    case T2S_W_LIN1_W: pack(wl + OFF_W1, FF, D, FF / 16); cvt_b16(wr + OFF_W1, (size_t)FF * D); break;
+    case T2S_W_LIN1_W: cvt_b16(wr + OFF_W1, (size_t)FF * D); break;  // packed by finalize_weights
     case T2S_W_LIN2_W: pack(wl + OFF_W2, D, FF, D / 16); cvt_b16(wr + OFF_W2, (size_t)D * FF); break;
     case T2S_W_IN_PROJ_B: cvt_f32(vl + VO_BQKV, 3 * D); break;
     case T2S_W_OUT_PROJ_B: cvt_f32(vl + VO_BO, D); break;
@@ -288,6 +295,7 @@ extern "C" int t2s_load_tensor(t2s_engine* e, int32_t id, int32_t layer, const v
   CK(cudaGetLastError());
   if (!on_device) { CK(cudaStreamSynchronize(s)); tmp.release(); }
   e->loaded[(size_t)id * (e->cfg.n_layer + 1) + (per_layer ? layer : 0)] = 1;
+  e->weights_final = false;
   return 0;
 }
 
@@ -298,6 +306,36 @@ static int check_loaded(t2s_engine* e) {
     for (int l = 0; l < (per_layer ? L : 1); ++l)
       if (!e->loaded[(size_t)id * (L + 1) + l]) return fail("weights incomplete: tensor id %d layer %d was never loaded", id, l);
   }
+  return 0;
+}
+
+// Folds every LayerNorm that precedes a projection into that projection's packed weights (phases.cuh) and
+// packs the folded matrices into MMA-fragment order.  Runs once after (re)loading weights.
+static int finalize_weights(t2s_engine* e, cudaStream_t s) {
+  if (e->weights_final) return 0;
+  const int L = e->cfg.n_layer;
+  const size_t GL = (size_t)(3 * D + FF) * D;  // folded row-major elements per layer
+  for (int l = 0; l < L; ++l) {
+    float* vl = e->wvec.as<float>() + (size_t)l * LV;
+    const float* vp = e->wvec.as<float>() + (size_t)(l > 0 ? l - 1 : 0) * LV;
+    const bf16* wr = e->wrow.as<bf16>() + (size_t)l * LW;
+    bf16* wg = e->wrow_g.as<bf16>() + (size_t)l * GL;
+    bf16* wl = e->wmat.as<bf16>() + (size_t)l * LW;
+    k_fold_ln<<<(3 * D + 7) / 8, 256, 0, s>>>(wr + OFF_WQKV, l > 0 ? vp + VO_G2 : nullptr, l > 0 ? vp + VO_BE2 : nullptr,
+                                            vl + VO_BQKV, wg, vl + VO_C1_QKV, vl + VO_C0_QKV, 3 * D, 3 * D);
+    k_pack_matrix<<<592, 256, 0, s>>>(wl + OFF_WQKV, wg, T2S_BF16, 3 * D, D, 3 * D / 16);
+    k_fold_ln<<<(FF + 7) / 8, 256, 0, s>>>(wr + OFF_W1, vl + VO_G1, vl + VO_BE1, vl + VO_B1, wg + (size_t)3 * D * D,
+                                         vl + VO_C1_FFN1, vl + VO_C0_FFN1, FF, FF);
+    k_pack_matrix<<<592, 256, 0, s>>>(wl + OFF_W1, wg + (size_t)3 * D * D, T2S_BF16, FF, D, FF / 16);
+    e->launches += 4;
+  }
+  const float* vlast = e->wvec.as<float>() + (size_t)(L - 1) * LV;
+  k_fold_ln<<<(VPAD + 7) / 8, 256, 0, s>>>(e->wrow_head.as<bf16>(), vlast + VO_G2, vlast + VO_BE2, nullptr,
+                                         e->wrow_head_g.as<bf16>(), e->head_c.as<float>(), e->head_c.as<float>() + VPAD, V, VPAD);
+  k_pack_matrix<<<592, 256, 0, s>>>(e->whead.as<bf16>(), e->wrow_head_g.as<bf16>(), T2S_BF16, VPAD, D, VT);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  e->weights_final = true;
   return 0;
 }
 
@@ -353,6 +391,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   if (!e || !rq) return fail("t2s_prefill: null argument");
   if (check_loaded(e)) return 1;
   cudaStream_t s = (cudaStream_t)stream_;
+  if (finalize_weights(e, s)) return 1;
   const int B = rq->batch, P = rq->prompt_len;
   if (B < 1 || B > e->cfg.max_batch) return fail("t2s_prefill: batch %d outside [1,%d]", B, e->cfg.max_batch);
   if (P < 0) return fail("t2s_prefill: negative prompt_len");
@@ -407,6 +446,11 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
   rc |= e->kvoff.ensure(R * 8);
   rc |= e->x0_rows.ensure((size_t)T * D * 4);
+  rc |= e->x0b_rows.ensure((size_t)T * D * 2);
+  rc |= e->yb1.ensure(R * D * 2);
+  rc |= e->yb2.ensure(R * D * 2);
+  rc |= e->sp1.ensure(R * 32 * 8);
+  rc |= e->sp2.ensure(R * 32 * 8);
   rc |= e->q.ensure(R * D * 4);
   rc |= e->attn.ensure(R * D * 2);
   rc |= e->y1.ensure(R * D * 4);
@@ -490,6 +534,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   // ---- contexts
   Ctx c{};
   c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
+  c.head_c1 = e->head_c.as<float>(); c.head_c0 = e->head_c.as<float>() + VPAD;
   c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
   c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
   c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
@@ -503,11 +548,12 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
   c.row_slot = e->d_row_slot; c.row_pos = e->d_row_pos; c.row_kvoff = e->kvoff.as<long long>();
   c.q = e->q.as<float>(); c.attn = e->attn.as<bf16>(); c.y1 = e->y1.as<float>(); c.h = e->h.as<bf16>();
+  c.yb1 = e->yb1.as<bf16>(); c.yb2 = e->yb2.as<bf16>(); c.sp1 = e->sp1.as<float2>(); c.sp2 = e->sp2.as<float2>();
   c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>(); c.logits = e->logits.as<float>();
   c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
   c.attn_desc = e->attn_desc.as<int>();
   c.attn_ctas = (e->decode_mode == 1 && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
-  c.probe = e->probe;
+
   c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
   c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
   c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
@@ -516,8 +562,8 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
   c.seen = e->seen.as<uint32_t>();
   c.timeline = e->timeline; c.tl_step = e->tl_step; c.tl_slots = e->tl_slots;
-  e->cp = c; e->cp.x0 = e->x0_rows.as<float>(); e->cp.x0_by_slot = 0; e->cp.head_rows = e->d_head_rows;
-  e->cd = c; e->cd.x0 = e->x0_slots.as<float>(); e->cd.x0_by_slot = 1; e->cd.head_rows = nullptr;
+  e->cp = c; e->cp.x0 = e->x0_rows.as<float>(); e->cp.x0b = e->x0b_rows.as<bf16>(); e->cp.x0_by_slot = 0; e->cp.head_rows = e->d_head_rows;
+  e->cd = c; e->cd.x0 = e->x0_slots.as<float>(); e->cd.x0b = e->x0b_slots.as<bf16>(); e->cd.x0_by_slot = 1; e->cd.head_rows = nullptr;
   const Ctx& cp = e->cp;
   // ---- launch
   CK(cudaEventRecord(e->ev0, s));
@@ -572,6 +618,8 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
       e->launches += 7;
     }
     if (!ok) return fail("t2s_prefill: cuTensorMapEncodeTiled failed");
+    k_rows_stats<<<(B + 7) / 8, 256, 0, s>>>(cp.y2, e->d_head_rows, B, cp.yb2, cp.sp2);
+    e->launches++;
   } else {
   for (int l = 0; l < cp.n_layer; ++l) {
       launch_phase<PH_QKV>(e, cp, l, g, s);
@@ -766,7 +814,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   c.top_p = top_p; c.temperature = temperature; c.rep_pen = repetition_penalty;
   c.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(seed >> 32);
   c.emb_audio = e->emb_audio.as<bf16>(); c.pe = e->pe.as<float>(); c.pe_len = e->cfg.pe_len; c.alpha_audio = 0.f;
-  c.x0 = e->x0_slots.as<float>();
+  c.x0 = e->x0_slots.as<float>(); c.x0b = e->x0b_slots.as<bf16>();
   launch_phase<PH_SAMPLE>(e, c, 0, std::min(n, e->num_sms), s);
   CK(cudaGetLastError());
   CK(cudaMemcpy2DAsync(tok_out, 4, c.sampled + step, (size_t)ms * 4, 4, n, cudaMemcpyDeviceToHost, s));
@@ -775,9 +823,9 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   return 0;
 }
 
-extern "C" int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots, long long* probe) {
+extern "C" int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots) {
   if (!e) return fail("null engine");
-  e->timeline = buf; e->tl_step = step; e->tl_slots = buf ? slots : 0; e->probe = buf ? probe : nullptr;
+  e->timeline = buf; e->tl_step = step; e->tl_slots = buf ? slots : 0;
   return 0;
 }
 

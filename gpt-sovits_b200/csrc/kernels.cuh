@@ -48,22 +48,22 @@ __global__ void __launch_bounds__(NT, 1) k_decode_persistent(Ctx c, int max_new_
   bar.init(c.bar, c.abort_flag, (unsigned)ncta);
   AttnSmem& as = *reinterpret_cast<AttnSmem*>(smem);
   SampSmem& ss = *reinterpret_cast<SampSmem*>(smem);
+  __shared__ int4 s_desc[2];  // this CTA's split-KV descriptors: fixed for all 24 layers of a step
   for (int it = 0; it < max_new_steps; ++it) {
     const int n = ld_cg_i(c.n_active);
     if (n == 0 || __ldcg(c.abort_flag) != 0) break;
+    if (threadIdx.x < 2) s_desc[threadIdx.x] = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + threadIdx.x);
+    __syncthreads();
     if (c.timeline) {
       const bool on = (it == c.tl_step);
       bar.tl = on ? c.timeline + (size_t)cta * c.tl_slots * 2 : nullptr;
       bar.tl_k = 0; bar.tl_n = c.tl_slots;
     }
     for (int layer = 0; layer < c.n_layer; ++layer) {
-      const bool probing = c.probe && bar.tl && layer == 1;
-      Probe p1{probing ? c.probe + (size_t)cta * 64 : nullptr, 0};
-      Probe p2{probing ? c.probe + (size_t)cta * 64 + 32 : nullptr, 0};
-      phase_qkv(c, layer, n, cta, ncta, smem, &p1);
+      phase_qkv(c, layer, n, cta, ncta, smem);
       prefetch_phase(c, PF_WO, layer, cta);  // attention has no weights: fetch the O-projection slice early
       bar.sync();
-      phase_attn_decode(c, layer, n, cta, ncta, as, &p2);
+      phase_attn_decode(c, layer, n, cta, ncta, as, s_desc);
       prefetch_phase(c, PF_W1, layer, cta);
       bar.sync();
       phase_oproj(c, layer, n, cta, ncta, smem);
@@ -134,13 +134,20 @@ __global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, co
     const long long ph = phoneme_ids[text_off[slot] + j];
     const bf16* er = c.emb_text + (size_t)ph * D;
     const float* pr = c.pe + (size_t)j * D;
-    for (int d = threadIdx.x; d < D; d += blockDim.x)
-      out[d] = __bfloat162float(er[d]) + c.bbert[d] + c.alpha_text * pr[d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float v = __bfloat162float(er[d]) + c.bbert[d] + c.alpha_text * pr[d];
+      out[d] = v;
+      c.x0b[(size_t)r * D + d] = __float2bfloat16_rn(v);  // text rows: overwritten with the final value by k_bert_proj
+    }
   } else {
     const long long tok = prompt[(long long)slot * prompt_row_stride + (j - L)];
     const bf16* er = c.emb_audio + (size_t)tok * D;
     const float* pr = c.pe + (size_t)(j - L) * D;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = __bfloat162float(er[d]) + c.alpha_audio * pr[d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float v = __bfloat162float(er[d]) + c.alpha_audio * pr[d];
+      out[d] = v;
+      c.x0b[(size_t)r * D + d] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(NT, 1) k_bert_proj(Ctx c, const bf16* bert_row
   ProjArgs a{};
   a.w = c.wbert; a.n_tiles = D / 16;
   a.in_b16 = bert_rows; a.out_idx = trow_row;
-  proj_phase<IN_BF16, OUT_BERT, 8, 1>(c, a, n_text_rows, blockIdx.x, gridDim.x, smem);
+  proj_phase<OUT_BERT, 8>(c, a, n_text_rows, blockIdx.x, gridDim.x, smem);
 }
 
 // ---- prefill attention with the prefix-LM mask (t2s_model.py:644-683 + SDPA :157) ------------------------
@@ -262,6 +269,54 @@ __global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_
   for (int i = threadIdx.x; i < c.max_steps; i += blockDim.x)
     o[c.P + i] = (i < n) ? (long long)c.gen[(size_t)b * c.max_steps + i] : -1ll;
   if (threadIdx.x == 0) idx_out[b] = idx;
+}
+
+// ---- LayerNorm folding and the prefill -> decode hand-off ---------------------------------------------------
+// Wg[f][k] = W[f][k] * gamma[k] (bf16), c1[f] = sum_k Wg[f][k], c0[f] = bias[f] + sum_k W[f][k] * beta[k].
+// gamma == NULL: no LayerNorm in front of this matrix (layer-0 QKV): Wg = W, c1 = 0, c0 = bias.
+// One warp per output feature; rows >= N (head padding) are zero.
+__global__ void k_fold_ln(const bf16* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ bias, bf16* __restrict__ wg, float* __restrict__ c1,
+                          float* __restrict__ c0, int N, int n_pad) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= n_pad) return;
+  float s1 = 0.f, s0 = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    float wv = 0.f, gv = 0.f;
+    if (f < N) {
+      wv = __bfloat162float(w[(size_t)f * D + k]);
+      const bf16 r = __float2bfloat16_rn(gamma ? wv * gamma[k] : wv);
+      gv = __bfloat162float(r);
+      wg[(size_t)f * D + k] = r;
+      if (beta) s0 += wv * beta[k];
+    } else {
+      wg[(size_t)f * D + k] = __float2bfloat16_rn(0.f);
+    }
+    s1 += gv;
+  }
+  s1 = warp_sum(s1); s0 = warp_sum(s0);
+  if (lane == 0) {
+    c1[f] = gamma ? s1 : 0.f;
+    c0[f] = (f < N && bias ? bias[f] : 0.f) + s0;
+  }
+}
+
+// After a tensor-core prefill the residual sums exist in fp32 only: give the B last rows (the head's input) the
+// bf16 copy + partial statistics the decode-side projections expect.  One warp per row.
+__global__ void k_rows_stats(const float* __restrict__ y, const int* __restrict__ rows, int n, bf16* __restrict__ yb,
+                             float2* __restrict__ sp) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int r = rows[i];
+  const float* src = y + (size_t)r * D + lane * 16;  // lane = 16-feature tile
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = src[j];
+    s += v; q += v * v;
+    yb[(size_t)r * D + lane * 16 + j] = __float2bfloat16_rn(v);
+  }
+  sp[(size_t)r * 32 + lane] = make_float2(s, q);
 }
 
 // ---- weight packing -----------------------------------------------------------------------------------

@@ -10,17 +10,8 @@
 
 namespace t2s {
 
-// measurement hook: thread 0 records SM clocks at named points of one phase instance
-struct Probe {
-  long long* buf;
-  int k;
-  __device__ __forceinline__ void mark() {
-    if (buf && threadIdx.x == 0 && k < 32) buf[k++] = clock64();
-  }
-};
-
 // =====================================================================================================
-// Skinny projections  Y[rows, features] = act(X[rows, K]) * W[features, K]^T
+// Skinny projections  Y[rows, features] = X[rows, K] * W[features, K]^T   (+ fused LayerNorm, epilogues)
 //
 // Work unit = one 16-feature tile over the whole K: its weights are one contiguous block (16 KB for
 // K=512, 64 KB for K=2048) stored in m16n8k16 A-fragment order, so a warp loads a fragment with one
@@ -29,233 +20,169 @@ struct Probe {
 // fixed order (no floating-point atomics anywhere: results are bit-reproducible) and the epilogue is
 // fused.  Units are spread over all CTAs, so every SM streams a disjoint slice of the weights; the next
 // phase's slice is prefetched into L2 before the grid barrier (prefetch_unit).
+//
+// Post-LN without an extra phase and without every consumer re-normalising fp32 rows: the PRODUCER of a
+// residual sum y (O-proj, FFN2) writes y in fp32, a bf16 copy, and per-16-feature-tile partial
+// (sum, sum of squares) of each row.  The CONSUMER stages the raw bf16 rows (half the bytes, no math),
+// rebuilds mean / rstd from the 32 partials, and applies LayerNorm in its epilogue:
+//     LN(y) W^T + b = rstd * (y Wg^T - mean * c1) + c0,   Wg = W * gamma,  c1 = Wg 1,  c0 = W beta + b
+// (gamma is folded into the packed weights once, k_fold_ln in kernels.cuh).
 // =====================================================================================================
-enum { IN_X0 = 0, IN_LN = 1, IN_BF16 = 2 };
 enum { OUT_QKV = 0, OUT_O = 1, OUT_FFN1 = 2, OUT_FFN2 = 3, OUT_HEAD = 4, OUT_BERT = 5 };
 
 // shared-memory carve-up for a projection with KBW k-blocks per warp (K = KBW*128)
-template <int KBW, int TPC = 1>
+template <int KBW>
 struct ProjLayout {
   static constexpr int K = KBW * 128;
   static constexpr int XSK = K + 8;  // bf16 row stride: (K+8)/2 words = 4 mod 32 -> conflict-free B fragments
   static constexpr size_t XS_BYTES = (size_t)RT * XSK * 2;
-  static constexpr size_t RED_BYTES = (size_t)NW * 16 * TPC * (RT + 1) * 4;
-  static constexpr size_t BYTES = XS_BYTES + RED_BYTES + RT * 8;
+  static constexpr size_t RED_BYTES = (size_t)NW * 16 * (RT + 1) * 4;
+  static constexpr size_t BYTES = XS_BYTES + RED_BYTES + RT * 8 + RT * 8;
   __device__ static bf16* xs(unsigned char* base) { return reinterpret_cast<bf16*>(base); }
   __device__ static float* red(unsigned char* base) { return reinterpret_cast<float*>(base + XS_BYTES); }
   __device__ static long long* kvoff(unsigned char* base) { return reinterpret_cast<long long*>(base + XS_BYTES + RED_BYTES); }
+  __device__ static float2* st(unsigned char* base) { return reinterpret_cast<float2*>(base + XS_BYTES + RED_BYTES + RT * 8); }
 };
-constexpr size_t SMEM_PROJ_MAX = ProjLayout<16, 1>::BYTES > ProjLayout<4, 2>::BYTES ? ProjLayout<16, 1>::BYTES : ProjLayout<4, 2>::BYTES;
+constexpr size_t SMEM_PROJ_MAX = ProjLayout<16>::BYTES;
 
 struct ProjArgs {
-  const bf16* w;       // packed weights of this matrix
-  int n_tiles;         // 16-feature tiles
-  const float* in_f32; // IN_X0 / IN_LN source rows [.,D]
-  const bf16* in_b16;  // IN_BF16 source rows [., K]
-  const int* in_idx;   // optional row gather for the fp32 sources
-  const float* ln_g;   // IN_LN
-  const float* ln_b;
-  // epilogue
-  const float* bias;
-  const float* res_g;  // OUT_O: LN params of the previous layer's norm2 (residual recompute)
+  const bf16* w;        // packed (gamma-folded) weights of this matrix
+  int n_tiles;          // 16-feature tiles
+  const bf16* in_b16;   // source rows [., K] bf16 (raw residual sums, or attention / FFN hidden)
+  const int* in_idx;    // optional row gather (layer-0 input by slot, head rows after prefill)
+  const float2* sp;     // partial row statistics of the source [., 32] -> LayerNorm folded in; NULL: no LN
+  const float* c1;      // LN: Wg 1
+  const float* c0;      // LN: W beta + bias;  no LN: bias (may be NULL)
+  const float* res_g;   // OUT_O: previous layer's norm2 (residual recompute)
   const float* res_b;
-  const float* b2;     // OUT_FFN1: linear2.bias for the y2 initialisation
-  const int* out_idx;  // OUT_BERT: text row -> prompt row
+  const float* g1;      // OUT_FFN1: this layer's norm1 + linear2.bias (y2 initialisation duty)
+  const float* be1;
+  const float* b2;
+  const int* out_idx;   // OUT_BERT: text row -> prompt row
   int layer;
 };
 
 // L2 prefetch of one unit's weight block (issued before a grid barrier for the NEXT phase)
 __device__ __forceinline__ void prefetch_unit(const bf16* w, int u, int k, int tpc) {
-  const size_t bytes = (size_t)16 * tpc * k * 2;  // (the head's last unit over-reads into its zero padding)
+  const size_t bytes = (size_t)16 * tpc * k * 2;
   const unsigned char* base = reinterpret_cast<const unsigned char*>(w) + (size_t)u * bytes;
   for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)NT * 128)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 
-template <int IN, int OUT, int KBW, int TPC>
-__device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, unsigned char* smem, int r0, int n_rows,
-                                           int u, const float (&g)[16], const float (&be)[16]) {
-  using LY = ProjLayout<KBW, TPC>;
+template <int OUT, int KBW>
+__device__ __forceinline__ void proj_stage(const Ctx& c, const ProjArgs& a, unsigned char* smem, int r0, int n_rows, int nt) {
+  using LY = ProjLayout<KBW>;
   bf16* xs = LY::xs(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (OUT == OUT_QKV && threadIdx.x < RT) {
-    const int r = r0 + threadIdx.x;
-    LY::kvoff(smem)[threadIdx.x] = (r < n_rows) ? __ldcg(c.row_kvoff + r) : 0ll;
+  constexpr int NR = RT / NW;                      // rows per warp
+  constexpr int CPL = LY::K / 256;                 // 16-byte chunks per lane per row
+  constexpr int RG = (16 / CPL) < NR ? (16 / CPL) : NR;  // rows in flight per warp (<= 16 loads per lane)
+  // ---- every independent load is issued first (volatile loads keep program order), consumed afterwards:
+  //      one L2 round trip instead of three (kv offsets, rows, statistics)
+  int ri[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int r = r0 + warp + NW * i;
+    ri[i] = (r < n_rows) ? (a.in_idx ? ld_cg_i(a.in_idx + r) : r) : -1;
   }
-  if (IN == IN_BF16) {
-    constexpr int CPL = LY::K / 256;               // 16-byte chunks per lane per row
-    constexpr int RG = (16 / CPL) < 4 ? (16 / CPL) : 4;  // rows in flight per warp
+  long long kvo = 0;
+  if (OUT == OUT_QKV && threadIdx.x < RT && r0 + (int)threadIdx.x < n_rows) kvo = ldv_cg_ll(c.row_kvoff + r0 + threadIdx.x);
+  float2 part[NR];
+  if (a.sp) {
 #pragma unroll
-    for (int i0 = 0; i0 < RT / NW; i0 += RG) {
-      uint4 v[RG][CPL];
+    for (int i = 0; i < NR; ++i) part[i] = (ri[i] >= 0) ? ldv_cg_f2(a.sp + (size_t)ri[i] * 32 + lane) : make_float2(0.f, 0.f);
+  }
 #pragma unroll
-      for (int i = 0; i < RG; ++i) {
-        const int r = r0 + warp + NW * (i0 + i);
-        const bf16* src = a.in_b16 + (size_t)r * LY::K;
+  for (int i0 = 0; i0 < NR; i0 += RG) {
+    uint4 v[RG][CPL];
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) v[i][j] = (r < n_rows) ? ld_cg16(src + (lane + 32 * j) * 8) : make_uint4(0, 0, 0, 0);
-      }
+    for (int i = 0; i < RG; ++i) {
+      const bf16* src = a.in_b16 + (size_t)max(ri[i0 + i], 0) * LY::K;
 #pragma unroll
-      for (int i = 0; i < RG; ++i) {
-        const int rl = warp + NW * (i0 + i);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) *reinterpret_cast<uint4*>(xs + rl * LY::XSK + (lane + 32 * j) * 8) = v[i][j];
-      }
+      for (int j = 0; j < CPL; ++j) v[i][j] = (ri[i0 + i] >= 0) ? ldv_cg16(src + (lane + 32 * j) * 8) : make_uint4(0, 0, 0, 0);
     }
-  } else {
-    // fp32 sources are always 512 wide: issue every load of this warp's 4 rows, then normalise
-    constexpr int NR = RT / NW;
-    int ri[NR];
+#pragma unroll
+    for (int i = 0; i < RG; ++i) {
+      const int rl = warp + NW * (i0 + i);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) *reinterpret_cast<uint4*>(xs + rl * LY::XSK + (lane + 32 * j) * 8) = v[i][j];
+    }
+  }
+  if (OUT == OUT_QKV && threadIdx.x < RT) LY::kvoff(smem)[threadIdx.x] = kvo;
+  if (a.sp) {
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int r = r0 + warp + NW * i;
-      ri[i] = (r < n_rows) ? (a.in_idx ? ld_cg_i(a.in_idx + r) : r) : -1;
-    }
-    float4 raw[NR][4];
-#pragma unroll
-    for (int i = 0; i < NR; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        raw[i][j] = (ri[i] >= 0) ? ld_cg_f4(a.in_f32 + (size_t)ri[i] * D + lane * 4 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      const int rl = warp + NW * i, r = r0 + rl;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(xs + rl * LY::XSK);
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { v[4 * j] = raw[i][j].x; v[4 * j + 1] = raw[i][j].y; v[4 * j + 2] = raw[i][j].z; v[4 * j + 3] = raw[i][j].w; }
-      if (IN == IN_LN && ri[i] >= 0) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s += v[j];
-        const float mean = warp_sum(s) * (1.0f / D);
-        float sq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { float d = v[j] - mean; sq += d * d; }
-        const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / D) + LN_EPS);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (v[j] - mean) * rstd * g[j] + be[j];
-        if (OUT == OUT_QKV && u == 0 && lane == 0) c.stat2[r] = make_float2(mean, rstd);
-        if (OUT == OUT_FFN1) {
-          // y2 := LN1(y1) + b2 on this unit's 4-feature slices (one per tile); FFN2 then adds its product
-#pragma unroll
-          for (int tt = 0; tt < TPC; ++tt) {
-            const int nt = u * TPC + tt;
-            if (lane == (nt & 31)) {
-              const int j = nt >> 5;
-              const float4 bb = *reinterpret_cast<const float4*>(a.b2 + 4 * nt);
-              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                if (jj == j) o = make_float4(v[4 * jj] + bb.x, v[4 * jj + 1] + bb.y, v[4 * jj + 2] + bb.z, v[4 * jj + 3] + bb.w);
-              *reinterpret_cast<float4*>(c.y2 + (size_t)r * D + 4 * nt) = o;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dst[(lane * 4 + 128 * j) / 2] = pack_bf2(v[4 * j], v[4 * j + 1]);
-        dst[(lane * 4 + 128 * j) / 2 + 1] = pack_bf2(v[4 * j + 2], v[4 * j + 3]);
+      const float s = warp_sum(part[i].x), q = warp_sum(part[i].y);
+      const float mean = s * (1.0f / D);
+      const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + LN_EPS);
+      if (lane == 0) {
+        const int rl = warp + NW * i;
+        LY::st(smem)[rl] = make_float2(mean, rstd);
+        if (OUT == OUT_QKV && nt == 0 && ri[i] >= 0) c.stat2[r0 + rl] = make_float2(mean, rstd);
       }
     }
   }
 }
 
-template <int OUT>
-__device__ __forceinline__ void proj_epilogue(const Ctx& c, const ProjArgs& a, const long long* kvoff, int r, int rl,
-                                              int f, float acc, float bias, float resg, float resb) {
-  if (OUT == OUT_QKV) {
-    const float val = acc + bias;
-    if (f < D) {
-      c.q[(size_t)r * D + f] = val * QSCALE;
-    } else {
-      const size_t off = (size_t)a.layer * c.kv_layer_stride + (size_t)kvoff[rl];
-      if (f < 2 * D) c.kpool[off + (f - D)] = __float2bfloat16_rn(val);
-      else c.vpool[off + (f - 2 * D)] = __float2bfloat16_rn(val);
-    }
-  } else if (OUT == OUT_O) {
-    float res;
-    if (a.layer == 0) {
-      const int ri = c.x0_by_slot ? ld_cg_i(c.row_slot + r) : r;
-      res = ld_cg_f(c.x0 + (size_t)ri * D + f);
-    } else {
-      const float2 st = __ldcg(c.stat2 + r);
-      res = (ld_cg_f(c.y2 + (size_t)r * D + f) - st.x) * st.y * resg + resb;
-    }
-    c.y1[(size_t)r * D + f] = res + bias + acc;
-  } else if (OUT == OUT_FFN1) {
-    c.h[(size_t)r * FF + f] = __float2bfloat16_rn(fmaxf(acc + bias, 0.f));
-  } else if (OUT == OUT_FFN2) {
-    float* p = c.y2 + (size_t)r * D + f;
-    *p = __ldcg(p) + acc;  // y2 was initialised to LN1(y1) + b2 by FFN1's staging; single writer
-  } else if (OUT == OUT_HEAD) {
-    if (f < V) c.logits[(size_t)r * VPAD + f] = acc;
-  } else if (OUT == OUT_BERT) {
-    float* p = c.x0 + (size_t)a.out_idx[r] * D + f;
-    *p = __ldcg(p) + acc;
+// 16-lane (one row, 16 features) reduction of (v, v*v): the producer's partial LayerNorm statistics
+__device__ __forceinline__ void row_partial_stats(float v, float2* dst, bool write) {
+  float s = v, q = v * v;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  if (write && (threadIdx.x & 15) == 0) *dst = make_float2(s, q);
 }
 
-// TPC = 16-feature tiles per unit (per CTA): 2 halves the number of CTAs that re-read every activation
-// row (the L2 broadcast is what bounds the staging step at batch >= 16) at no cost in weight bytes.
-template <int IN, int OUT, int KBW, int TPC>
-__device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta, int ncta, unsigned char* smem,
-                           Probe* pr = nullptr) {
-  using LY = ProjLayout<KBW, TPC>;
+template <int OUT, int KBW>
+__device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta, int ncta, unsigned char* smem) {
+  using LY = ProjLayout<KBW>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   constexpr int KB_ROW = KBW * NW;  // k-blocks per feature tile
-  constexpr int FU = 16 * TPC;      // features per unit
   bf16* xs = LY::xs(smem);
-  float (*red)[FU][RT + 1] = reinterpret_cast<float (*)[FU][RT + 1]>(LY::red(smem));
+  float (*red)[16][RT + 1] = reinterpret_cast<float (*)[16][RT + 1]>(LY::red(smem));
   const long long* kvoff = LY::kvoff(smem);
-  float lg[16], lb[16];
-  if (IN == IN_LN) {
+  const float2* st = LY::st(smem);
+  const bool ln = a.sp != nullptr;
+  for (int nt = cta; nt < a.n_tiles; nt += ncta) {
+    // this warp's KBW A fragments (k-blocks warp*KBW .. +KBW-1 of feature tile nt), loaded once per unit
+    uint4 af[KBW];
+    const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * KB_ROW + warp * KBW) * 32 + lane;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float4 x = *reinterpret_cast<const float4*>(a.ln_g + lane * 4 + 128 * j);
-      float4 y = *reinterpret_cast<const float4*>(a.ln_b + lane * 4 + 128 * j);
-      lg[4 * j] = x.x; lg[4 * j + 1] = x.y; lg[4 * j + 2] = x.z; lg[4 * j + 3] = x.w;
-      lb[4 * j] = y.x; lb[4 * j + 1] = y.y; lb[4 * j + 2] = y.z; lb[4 * j + 3] = y.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { lg[j] = 1.f; lb[j] = 0.f; }
-  }
-  if (pr) pr->mark();
-  const int n_units = (a.n_tiles + TPC - 1) / TPC;
-  for (int u = cta; u < n_units; u += ncta) {
-    // this warp's A fragments (k-blocks warp*KBW .. +KBW-1 of each feature tile), loaded once per unit
-    uint4 af[TPC][KBW];
-#pragma unroll
-    for (int tt = 0; tt < TPC; ++tt) {
-      const int nt = min(u * TPC + tt, a.n_tiles - 1);  // a ragged last unit re-reads a valid tile (result discarded)
-      const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * KB_ROW + warp * KBW) * 32 + lane;
-#pragma unroll
-      for (int i = 0; i < KBW; ++i) af[tt][i] = ld_weight16(wp + i * 32);
-    }
-    // per-thread epilogue constants: this thread always reduces feature u*FU + (tid % FU)
-    const int fme = u * FU + (threadIdx.x % FU);
-    const bool fok = fme < a.n_tiles * 16;
-    const float bias = (a.bias && fok) ? a.bias[fme] : 0.f;
+    for (int i = 0; i < KBW; ++i) af[i] = ld_weight16(wp + i * 32);
+    // per-thread epilogue constants: this thread always reduces feature nt*16 + (tid & 15)
+    const int fme = nt * 16 + (threadIdx.x & 15);
+    const float c0 = a.c0 ? a.c0[fme] : 0.f;
+    const float c1 = ln ? a.c1[fme] : 0.f;
     const float resg = (OUT == OUT_O && a.res_g) ? a.res_g[fme] : 1.f;
     const float resb = (OUT == OUT_O && a.res_b) ? a.res_b[fme] : 0.f;
     for (int r0 = 0; r0 < n_rows; r0 += RT) {
       const int rows_here = min(RT, n_rows - r0);
       const int n8 = (rows_here + 7) >> 3;
-      __syncthreads();  // previous readers of xs / red / kvoff are done
-      if (pr) pr->mark();
-      proj_stage<IN, OUT, KBW, TPC>(c, a, smem, r0, n_rows, u, lg, lb);
+      __syncthreads();  // previous readers of xs / red / kvoff / st are done
+      proj_stage<OUT, KBW>(c, a, smem, r0, n_rows, nt);
       __syncthreads();
-      if (pr) pr->mark();
-      float acc[TPC][4][4];
+      if (OUT == OUT_FFN1 && threadIdx.x < rows_here) {
+        // duty of FFN1's unit nt: y2[:, 4nt..4nt+3] := LN1(y1) + b2 (FFN2 then adds its product; single writer)
+        const int r = r0 + threadIdx.x;
+        const float2 s2 = st[threadIdx.x];
+        const float4 y = ld_cg_f4(c.y1 + (size_t)r * D + 4 * nt);
+        const float4 gg = *reinterpret_cast<const float4*>(a.g1 + 4 * nt);
+        const float4 bb = *reinterpret_cast<const float4*>(a.be1 + 4 * nt);
+        const float4 b2 = *reinterpret_cast<const float4*>(a.b2 + 4 * nt);
+        *reinterpret_cast<float4*>(c.y2 + (size_t)r * D + 4 * nt) =
+            make_float4((y.x - s2.x) * s2.y * gg.x + bb.x + b2.x, (y.y - s2.x) * s2.y * gg.y + bb.y + b2.y,
+                        (y.z - s2.x) * s2.y * gg.z + bb.z + b2.z, (y.w - s2.x) * s2.y * gg.w + bb.w + b2.w);
+      }
+      float acc[4][4];
 #pragma unroll
-      for (int tt = 0; tt < TPC; ++tt)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[tt][i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
       for (int i = 0; i < KBW; ++i) {
         const int k0 = (warp * KBW + i) * 16;
@@ -263,95 +190,133 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
         for (int n = 0; n < 4; ++n) {
           if (n < n8) {
             const uint32_t* xr = reinterpret_cast<const uint32_t*>(xs + (n * 8 + g) * LY::XSK + k0);
-            const uint32_t b0 = xr[t], b1 = xr[4 + t];
-#pragma unroll
-            for (int tt = 0; tt < TPC; ++tt) mma_bf16_16816(acc[tt][n], af[tt][i], b0, b1);
+            mma_bf16_16816(acc[n], af[i], xr[t], xr[4 + t]);
           }
         }
       }
 #pragma unroll
-      for (int tt = 0; tt < TPC; ++tt)
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          red[warp][tt * 16 + g][n * 8 + 2 * t] = acc[tt][n][0];
-          red[warp][tt * 16 + g][n * 8 + 2 * t + 1] = acc[tt][n][1];
-          red[warp][tt * 16 + g + 8][n * 8 + 2 * t] = acc[tt][n][2];
-          red[warp][tt * 16 + g + 8][n * 8 + 2 * t + 1] = acc[tt][n][3];
-        }
+      for (int n = 0; n < 4; ++n) {
+        red[warp][g][n * 8 + 2 * t] = acc[n][0];
+        red[warp][g][n * 8 + 2 * t + 1] = acc[n][1];
+        red[warp][g + 8][n * 8 + 2 * t] = acc[n][2];
+        red[warp][g + 8][n * 8 + 2 * t + 1] = acc[n][3];
+      }
       __syncthreads();
-      if (pr) pr->mark();
-      if (fok) {
 #pragma unroll
-        for (int o = threadIdx.x; o < FU * RT; o += NT) {
-          const int fl = o % FU, n = o / FU;
-          if (n < rows_here) {
-            float s = 0.f;
+      for (int it = 0; it < 16 * RT / NT; ++it) {
+        const int o = threadIdx.x + it * NT;
+        const int fl = o & 15, n = o >> 4;  // a 16-lane group = one row, 16 features
+        const bool ok = n < rows_here;
+        const int r = r0 + n, f = nt * 16 + fl;
+        float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += red[w][fl][n];
-            proj_epilogue<OUT>(c, a, kvoff, r0 + n, n, u * FU + fl, s, bias, resg, resb);
+        for (int w = 0; w < NW; ++w) s += red[w][fl][n];
+        float val = s + c0;
+        if (ln) { const float2 s2 = st[n]; val = s2.y * (s - s2.x * c1) + c0; }
+        if (OUT == OUT_QKV) {
+          if (ok) {
+            if (f < D) {
+              c.q[(size_t)r * D + f] = val * QSCALE;
+            } else {
+              const size_t off = (size_t)a.layer * c.kv_layer_stride + (size_t)kvoff[n];
+              if (f < 2 * D) c.kpool[off + (f - D)] = __float2bfloat16_rn(val);
+              else c.vpool[off + (f - 2 * D)] = __float2bfloat16_rn(val);
+            }
+          }
+        } else if (OUT == OUT_O) {
+          float y = 0.f;
+          if (ok) {
+            float res;
+            if (a.layer == 0) {
+              const int ri = c.x0_by_slot ? ld_cg_i(c.row_slot + r) : r;
+              res = ld_cg_f(c.x0 + (size_t)ri * D + f);
+            } else {
+              const float2 s2 = __ldcg(c.stat2 + r);
+              res = (ld_cg_f(c.y2 + (size_t)r * D + f) - s2.x) * s2.y * resg + resb;
+            }
+            y = res + val;
+            c.y1[(size_t)r * D + f] = y;
+            c.yb1[(size_t)r * D + f] = __float2bfloat16_rn(y);
+          }
+          row_partial_stats(y, c.sp1 + (size_t)r * 32 + nt, ok);
+        } else if (OUT == OUT_FFN1) {
+          if (ok) c.h[(size_t)r * FF + f] = __float2bfloat16_rn(fmaxf(val, 0.f));
+        } else if (OUT == OUT_FFN2) {
+          float y = 0.f;
+          if (ok) {
+            float* p = c.y2 + (size_t)r * D + f;
+            y = __ldcg(p) + s;  // y2 was initialised to LN1(y1) + b2 by FFN1's duty; single writer
+            *p = y;
+            c.yb2[(size_t)r * D + f] = __float2bfloat16_rn(y);
+          }
+          row_partial_stats(y, c.sp2 + (size_t)r * 32 + nt, ok);
+        } else if (OUT == OUT_HEAD) {
+          if (ok && f < V) c.logits[(size_t)r * VPAD + f] = val;
+        } else if (OUT == OUT_BERT) {
+          if (ok) {
+            const size_t o2 = (size_t)a.out_idx[r] * D + f;
+            const float y = __ldcg(c.x0 + o2) + s;
+            c.x0[o2] = y;
+            c.x0b[o2] = __float2bfloat16_rn(y);
           }
         }
       }
-      if (pr) pr->mark();
     }
   }
 }
 
 // ---- the five per-layer projection phases + head, with their argument wiring ------------------------
-__device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm,
-                                          Probe* pr = nullptr) {
+__device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WQKV;
   a.n_tiles = 3 * D / 16; a.layer = layer;
-  a.bias = c.wvec + (size_t)layer * LV + VO_BQKV;
+  a.c0 = c.wvec + (size_t)layer * LV + VO_C0_QKV;  // = in_proj_bias for layer 0
   if (layer == 0) {
-    a.in_f32 = c.x0; a.in_idx = c.x0_by_slot ? c.row_slot : nullptr;
-    proj_phase<IN_X0, OUT_QKV, 4, 1>(c, a, n_rows, cta, ncta, sm, pr);
+    a.in_b16 = c.x0b; a.in_idx = c.x0_by_slot ? c.row_slot : nullptr;
   } else {
-    a.in_f32 = c.y2;
-    a.ln_g = c.wvec + (size_t)(layer - 1) * LV + VO_G2;
-    a.ln_b = c.wvec + (size_t)(layer - 1) * LV + VO_BE2;
-    proj_phase<IN_LN, OUT_QKV, 4, 1>(c, a, n_rows, cta, ncta, sm, pr);
+    a.in_b16 = c.yb2; a.sp = c.sp2;
+    a.c1 = c.wvec + (size_t)layer * LV + VO_C1_QKV;
   }
+  proj_phase<OUT_QKV, 4>(c, a, n_rows, cta, ncta, sm);
 }
 __device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WO;
   a.n_tiles = D / 16; a.layer = layer;
   a.in_b16 = c.attn;
-  a.bias = c.wvec + (size_t)layer * LV + VO_BO;
+  a.c0 = c.wvec + (size_t)layer * LV + VO_BO;
   if (layer > 0) {
     a.res_g = c.wvec + (size_t)(layer - 1) * LV + VO_G2;
     a.res_b = c.wvec + (size_t)(layer - 1) * LV + VO_BE2;
   }
-  proj_phase<IN_BF16, OUT_O, 4, 1>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<OUT_O, 4>(c, a, n_rows, cta, ncta, sm);
 }
 __device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W1;
   a.n_tiles = FF / 16; a.layer = layer;
-  a.in_f32 = c.y1;
-  a.ln_g = c.wvec + (size_t)layer * LV + VO_G1;
-  a.ln_b = c.wvec + (size_t)layer * LV + VO_BE1;
-  a.bias = c.wvec + (size_t)layer * LV + VO_B1;
+  a.in_b16 = c.yb1; a.sp = c.sp1;
+  a.c1 = c.wvec + (size_t)layer * LV + VO_C1_FFN1;
+  a.c0 = c.wvec + (size_t)layer * LV + VO_C0_FFN1;
+  a.g1 = c.wvec + (size_t)layer * LV + VO_G1;
+  a.be1 = c.wvec + (size_t)layer * LV + VO_BE1;
   a.b2 = c.wvec + (size_t)layer * LV + VO_B2;
-  proj_phase<IN_LN, OUT_FFN1, 4, 1>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<OUT_FFN1, 4>(c, a, n_rows, cta, ncta, sm);
 }
 __device__ __forceinline__ void phase_ffn2(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W2;
   a.n_tiles = D / 16; a.layer = layer;
   a.in_b16 = c.h;
-  proj_phase<IN_BF16, OUT_FFN2, 16, 1>(c, a, n_rows, cta, ncta, sm);
+  proj_phase<OUT_FFN2, 16>(c, a, n_rows, cta, ncta, sm);
 }
 __device__ __forceinline__ void phase_head(const Ctx& c, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.whead;
   a.n_tiles = VT; a.layer = c.n_layer;
-  a.in_f32 = c.y2; a.in_idx = c.head_rows;
-  a.ln_g = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_G2;
-  a.ln_b = c.wvec + (size_t)(c.n_layer - 1) * LV + VO_BE2;
-  proj_phase<IN_LN, OUT_HEAD, 4, 1>(c, a, n_rows, cta, ncta, sm);
+  a.in_b16 = c.yb2; a.sp = c.sp2; a.in_idx = c.head_rows;
+  a.c1 = c.head_c1; a.c0 = c.head_c0;
+  proj_phase<OUT_HEAD, 4>(c, a, n_rows, cta, ncta, sm);
 }
 
 // L2 prefetch of this CTA's K/V position ranges of `layer` (issued during the QKV phase, one grid barrier
@@ -361,11 +326,10 @@ __device__ __forceinline__ void prefetch_kv(const Ctx& c, int layer, int cta) {
   const int e = tid >> 7, i = tid & 127;  // descriptor entry, page-run index
   const int4 ds = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
   if (ds.x < 0) return;
-  const int pbeg = ds.y, pend = ds.z;
+  const int pbeg = ds.y, pend = ds.z, slot = ds.x >> 16;
   const int p0 = (pbeg & ~(PAGE - 1)) + (i >> 1) * PAGE;  // page-aligned run start; even i: K, odd i: V
   if (p0 >= pend) return;
   const int a0 = max(p0, pbeg), a1 = min(p0 + PAGE, pend);
-  const int slot = ld_cg_i(c.row_slot + ds.x);
   const int page = c.page_table[slot * c.max_pages + (a0 >> 6)];
   const bf16* base = ((i & 1) ? c.vpool : c.kpool) + (size_t)layer * c.kv_layer_stride +
                      ((size_t)page * PAGE + (a0 & (PAGE - 1))) * D;
@@ -533,15 +497,14 @@ __device__ __forceinline__ void attn_segment(const Ctx& c, int layer, int slot, 
 // The split-KV work assignment is the same for all layers of a step, so phase_plan computes it once:
 // every CTA gets at most two descriptors {row, pbeg, pend, (j << 16) | count}: its j-th of `count`
 // position ranges of `row`.  A row's partials live in c.part[first_cta .. first_cta + count).
-__device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, int ncta, AttnSmem& sm, Probe* pr = nullptr) {
+__device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, int ncta, AttnSmem& sm,
+                                  const int4* cached_desc = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (pr) pr->mark();
   for (int e = 0; e < 2; ++e) {
-    const int4 ds = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
-    const int r = ds.x;
-    if (r < 0) break;
+    const int4 ds = cached_desc ? cached_desc[e] : __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
+    if (ds.x < 0) break;
+    const int r = ds.x & 0xFFFF, slot = ds.x >> 16;
     const int pbeg = ds.y, pend = ds.z, j = ds.w >> 16, count = ds.w & 0xFFFF;
-    const int slot = ld_cg_i(c.row_slot + r);
     float qa[8], qb[8];
     {
       const float* qr = c.q + (size_t)r * D;
@@ -550,14 +513,12 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
       qa[0] = x0.x; qa[1] = x0.y; qa[2] = x0.z; qa[3] = x0.w; qa[4] = x1.x; qa[5] = x1.y; qa[6] = x1.z; qa[7] = x1.w;
       qb[0] = y0.x; qb[1] = y0.y; qb[2] = y0.z; qb[3] = y0.w; qb[4] = y1.x; qb[5] = y1.y; qb[6] = y1.z; qb[7] = y1.w;
     }
-    if (pr) pr->mark();
-    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, accA[8], accB[8];
+      float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, accA[8], accB[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
     if (pend - pbeg > 16) attn_segment<4>(c, layer, slot, pbeg, pend, qa, qb, m, l, accA, accB);
     else attn_segment<1>(c, layer, slot, pbeg, pend, qa, qb, m, l, accA, accB);
-    if (pr) pr->mark();
-    __syncthreads();  // previous entry's merge readers are done with sm.m/l/acc
+      __syncthreads();  // previous entry's merge readers are done with sm.m/l/acc
     if ((lane & 3) == 0) {
       sm.m[warp][lane >> 2] = m[0]; sm.l[warp][lane >> 2] = l[0];
       sm.m[warp][8 + (lane >> 2)] = m[1]; sm.l[warp][8 + (lane >> 2)] = l[1];
@@ -566,8 +527,7 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
     for (int i = 0; i < 8; ++i) { sm.acc[warp][lane * 8 + i] = accA[i]; sm.acc[warp][256 + lane * 8 + i] = accB[i]; }
     __syncthreads();
     attn_merge_write(c, sm, r, cta, count);
-    if (pr) pr->mark();
-    if (count > 1) {
+      if (count > 1) {
       __syncthreads();
       if (tid == 0) {
         // release our partial, acquire the others' (acq_rel RMW at gpu scope)
@@ -576,8 +536,7 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
         sm.scratch[NW] = (old == count - 1);
       }
       __syncthreads();
-      if (pr) pr->mark();
-      if (sm.scratch[NW]) {  // last CTA of this sequence: merge all partials (count <= 16)
+          if (sm.scratch[NW]) {  // last CTA of this sequence: merge all partials (count <= 16)
         const float* pbase = c.part + (size_t)(cta - j) * PART_STRIDE;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -605,8 +564,7 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
         }
         if (tid == 0) c.seg_cnt[r] = 0;
       }
-      if (pr) pr->mark();
-    }
+        }
   }
 }
 
@@ -900,7 +858,9 @@ __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, Samp
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int d = tid + NT * k;
-        c.x0[(size_t)slot * D + d] = __bfloat162float(er[d]) + c.alpha_audio * pr[d];
+        const float xv = __bfloat162float(er[d]) + c.alpha_audio * pr[d];
+        c.x0[(size_t)slot * D + d] = xv;
+        c.x0b[(size_t)slot * D + d] = __float2bfloat16_rn(xv);
       }
     }
     __syncthreads();
@@ -944,7 +904,8 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
   }
   // ---- split-KV work assignment for the next step's attention (valid for all layers)
   int* np_s = smem_i + 16;        // [MAX_B] positions per new row
-  if (keep) np_s[woff + inc - 1] = (int)kvpos;
+  int* slot_s = smem_i + 16 + MAX_B;  // [MAX_B] slot of each new row
+  if (keep) { np_s[woff + inc - 1] = (int)kvpos; slot_s[woff + inc - 1] = slot; }
   const int ncta = c.attn_ctas;
   int4* desc = reinterpret_cast<int4*>(c.attn_desc);
   for (int i = tid; i < 2 * ncta; i += NT) desc[i] = make_int4(-1, 0, 0, 0);
@@ -952,7 +913,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
   const int n2 = total;
   if (n2 == 0) return;
   if (n2 > ncta) {  // more rows than CTAs: whole rows, round-robin (n2 <= MAX_B < 2 * ncta)
-    if (tid < n2) desc[(tid % ncta) * 2 + tid / ncta] = make_int4(tid, 0, np_s[tid], 1);
+    if (tid < n2) desc[(tid % ncta) * 2 + tid / ncta] = make_int4(tid | (slot_s[tid] << 16), 0, np_s[tid], 1);
     return;
   }
   // Np
@@ -987,7 +948,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     const int q = (((v + k - 1) / k) + 7) & ~7;  // positions per CTA, multiple of 8
     const int count = (v + q - 1) / q;
     for (int jj = 0; jj < count; ++jj)
-      desc[(c0 + jj) * 2] = make_int4(tid, jj * q, min(v, (jj + 1) * q), (jj << 16) | count);
+      desc[(c0 + jj) * 2] = make_int4(tid | (slot_s[tid] << 16), jj * q, min(v, (jj + 1) * q), (jj << 16) | count);
   }
 }
 

@@ -141,9 +141,8 @@ int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, int32_t widt
 
 /* Measurement hook: during persistent-kernel iteration `step` of the next t2s_decode, thread 0 of every CTA
  * records its SM clock when it arrives at / is released from each grid barrier:
- * buf[cta][slots][2] (device, int64); probe[cta][2][32] (device, int64, optional) receives intra-phase marks
- * of layer 1's QKV and attention phases.  Set before t2s_prefill; NULL clears. */
-int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots, long long* probe);
+ * buf[cta][slots][2] (device, int64).  Set before t2s_prefill; NULL clears. */
+int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots);
 
 /* Measurement hook: latency of n_barriers back-to-back grid barriers of the persistent kernel. */
 int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* ms_out, void* stream);

@@ -15,8 +15,7 @@ eng = gsb.T2SEngine(synthetic.S1V2_CONFIG); eng.load_state_dict(sd, pe=synthetic
 nb = 24 * 5 + 3
 ncta = int(eng.stats()["num_sms"])
 tl = torch.zeros((ncta, nb, 2), dtype=torch.int64, device="cuda")
-probe = torch.zeros((ncta, 2, 32), dtype=torch.int64, device="cuda")
-_lib.check(eng.lib.t2s_set_timeline(eng._h, tl.data_ptr(), a.at, nb, probe.data_ptr()))
+_lib.check(eng.lib.t2s_set_timeline(eng._h, tl.data_ptr(), a.at, nb))
 L = synthetic.config_lens(a.batch, a.lo, a.hi, seed=100)
 ids, lens, prompt, bert = synthetic.make_inputs(a.batch, L, a.prompt, seed=200)
 r = eng.infer([t.cuda() for t in ids], [t.cuda() for t in bert], prompt.cuda(), top_k=15, early_stop_num=a.steps, seed=1)
@@ -42,13 +41,3 @@ for k in range(nb):
 print("mean phase time (us):", {k: round(float(np.mean(v)), 2) for k, v in tot.items()})
 print("step total (us):", round(sum(sum(v) for v in tot.values()), 1))
 
-pb = probe.cpu().numpy().astype(np.float64)
-for ph, nm in ((0, "qkv L1 marks: start, pre-stage, post-stage, post-mma+red, end"), (1, "attn L1 marks: start, q loaded, segment done, merged+partial, after atomic, after final merge")):
-    x = pb[:, ph, :]
-    valid = (x > 0).sum(axis=1)
-    print(nm)
-    for nmarks in sorted(set(valid.tolist())):
-        if nmarks < 2: continue
-        sel = x[valid == nmarks][:, :nmarks]
-        d = np.diff(sel, axis=1) / MHZ
-        print(f"   {len(sel):3d} CTAs with {nmarks} marks: mean deltas (us) {np.round(d.mean(axis=0), 2)}  max total {np.round(((sel[:, -1]-sel[:, 0])/MHZ).max(), 2)}")
