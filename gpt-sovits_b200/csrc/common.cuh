@@ -200,7 +200,11 @@ struct GridBarrier {
       unsigned spins = 0;
       long long t0 = 0;
       for (;;) {
+#ifdef T2S_BAR_ACQ_POLL
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+#else
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+#endif
         if (v >= target) break;
         if ((++spins & 0x3FFu) == 0) {
           long long now = clock64();
@@ -211,7 +215,9 @@ struct GridBarrier {
           }
         }
       }
+#ifndef T2S_BAR_ACQ_POLL
       asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire side of the relaxed poll
+#endif
       if (tl && tl_k < tl_n) { tl[2 * tl_k + 1] = clock64(); ++tl_k; }
     }
     __syncthreads();

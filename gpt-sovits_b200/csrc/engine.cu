@@ -92,7 +92,8 @@ struct t2s_engine {
   int n_logits_rec = 0;
   long long* timeline = nullptr;
   int tl_step = 0, tl_slots = 0;
-  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16;
+  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16, tc_decode_min_batch = 160;
+  int graph_mode = -1;
   bool tc_ok = false;
   DevBuf xf, xb;  // tcgen05 prefill path: LayerNorm'ed rows (fp32 residual + bf16 GEMM operand)
   // graph cache (decode_mode 0)
@@ -343,12 +344,13 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
 extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
-    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 2) return fail("decode mode must be 0, 1 or 2"); e->decode_mode = (int)v; break;
+    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 3) return fail("decode mode must be 0, 1, 2 or 3"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM:
       if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
       if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
       e->prefill_gemm = (int)v; break;
     case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
+    case T2S_OPT_TC_DECODE_MIN_BATCH: if (v < 0 || v > 100000) return fail("tc_decode_min_batch out of range"); e->tc_decode_min_batch = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
   }
@@ -384,6 +386,51 @@ static void launch_decode_step(t2s_engine* e, const Ctx& c, cudaStream_t s) {
   launch_phase<PH_HEAD>(e, c, 0, g, s);
   launch_phase<PH_SAMPLE>(e, c, 0, std::min(std::max(c.B0, 1), g), s);
   launch_phase<PH_PLAN>(e, c, 0, 1, s);
+}
+
+// Large-batch decode step: projections on the tensor cores (k_gemm_tc<64>, LayerNorm folded into the epilogue,
+// A operand = the bf16 activations the previous kernel's epilogue wrote, fetched by TMA), attention / head /
+// sampler / plan as phase kernels.  Captured into a CUDA graph by t2s_decode.
+static bool launch_decode_step_tc(t2s_engine* e, const Ctx& c, cudaStream_t s) {
+  const int g = e->num_sms, B0 = c.B0;
+  float* x0r = e->x0_rows.as<float>();
+  bf16* x0br = e->x0b_rows.as<bf16>();
+  const size_t GL = (size_t)(3 * D + FF) * D;
+  k_gather_x0<<<B0, 128, 0, s>>>(c, x0r, x0br);
+  e->launches++;
+  bool ok = true;
+  for (int l = 0; l < c.n_layer && ok; ++l) {
+    const float* vl = c.wvec + (size_t)l * LV;
+    const float* vp = c.wvec + (size_t)(l > 0 ? l - 1 : 0) * LV;
+    const bf16* wr = e->wrow.as<bf16>() + (size_t)l * LW;
+    const bf16* wg = e->wrow_g.as<bf16>() + (size_t)l * GL;
+    TcEpilogue ep{};
+    ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
+    ep.mode = EPI_D_QKV; ep.bias = vl + VO_C0_QKV; ep.c1 = vl + VO_C1_QKV; ep.sp_in = l > 0 ? c.sp2 : nullptr;
+    ep.stat_out = l > 0 ? c.stat2 : nullptr; ep.out_f32 = c.q; ep.kpool = c.kpool; ep.vpool = c.vpool;
+    ep.kvoff = c.row_kvoff; ep.layer_off = (size_t)l * c.kv_layer_stride;
+    ok = ok && launch_gemm_tc<64>(l == 0 ? x0br : c.yb2, wg, B0, 3 * D, D, ep, s);
+    launch_phase<PH_ATTN>(e, c, l, g, s);
+    ep = TcEpilogue{};
+    ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
+    ep.mode = EPI_D_O; ep.bias = vl + VO_BO; ep.src_f32 = l == 0 ? x0r : c.y2; ep.stat_in = l == 0 ? nullptr : c.stat2;
+    ep.g = vp + VO_G2; ep.be = vp + VO_BE2; ep.out_f32 = c.y1; ep.out_b16 = c.yb1; ep.sp_out = c.sp1;
+    ok = ok && launch_gemm_tc<64>(c.attn, wr + OFF_WO, B0, D, D, ep, s);
+    ep = TcEpilogue{};
+    ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
+    ep.mode = EPI_D_FFN1; ep.bias = vl + VO_C0_FFN1; ep.c1 = vl + VO_C1_FFN1; ep.sp_in = c.sp1; ep.out_b16 = c.h;
+    ok = ok && launch_gemm_tc<64>(c.yb1, wg + (size_t)3 * D * D, B0, FF, D, ep, s);
+    ep = TcEpilogue{};
+    ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
+    ep.mode = EPI_D_FFN2; ep.src_f32 = c.y1; ep.sp_res = c.sp1; ep.g = vl + VO_G1; ep.be = vl + VO_BE1; ep.b2 = vl + VO_B2;
+    ep.out_f32 = c.y2; ep.out_b16 = c.yb2; ep.sp_out = c.sp2;
+    ok = ok && launch_gemm_tc<64>(c.h, wr + OFF_W2, B0, D, FF, ep, s);
+    e->launches += 4;
+  }
+  launch_phase<PH_HEAD>(e, c, 0, g, s);
+  launch_phase<PH_SAMPLE>(e, c, 0, std::min(std::max(c.B0, 1), g), s);
+  launch_phase<PH_PLAN>(e, c, 0, 1, s);
+  return ok;
 }
 
 // ---- prefill ---------------------------------------------------------------------------------------------
@@ -604,17 +651,17 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
       ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
-      ok = ok && launch_gemm_tc(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
+      ok = ok && launch_gemm_tc<128>(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
       k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
       ep = TcEpilogue{};
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;
-      ok = ok && launch_gemm_tc(cp.attn, wr + OFF_WO, T, D, D, ep, s);
+      ok = ok && launch_gemm_tc<128>(cp.attn, wr + OFF_WO, T, D, D, ep, s);
       k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.y1, vl + VO_G1, vl + VO_BE1, xf, xb, T, 1);
       ep.mode = EPI_RELU; ep.bias = vl + VO_B1; ep.resid = nullptr; ep.out_f32 = nullptr; ep.out_b16 = cp.h;
-      ok = ok && launch_gemm_tc(xb, wr + OFF_W1, T, FF, D, ep, s);
+      ok = ok && launch_gemm_tc<128>(xb, wr + OFF_W1, T, FF, D, ep, s);
       ep.mode = EPI_RESID; ep.bias = vl + VO_B2; ep.resid = xf; ep.out_f32 = cp.y2; ep.out_b16 = nullptr;
-      ok = ok && launch_gemm_tc(cp.h, wr + OFF_W2, T, D, FF, ep, s);
+      ok = ok && launch_gemm_tc<128>(cp.h, wr + OFF_W2, T, D, FF, ep, s);
       e->launches += 7;
     }
     if (!ok) return fail("t2s_prefill: cuTensorMapEncodeTiled failed");
@@ -665,7 +712,11 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   int budget = max_new_steps < 0 ? e->max_steps : max_new_steps;
   CK(cudaEventRecord(e->ev0, s));
   if (n_active > 0 && budget > 0) {
-    if (e->decode_mode == 1) {
+    int mode = e->decode_mode;
+    if (mode == 1 && e->tc_ok && e->tc_decode_min_batch > 0 && e->B >= e->tc_decode_min_batch) mode = 3;
+    if (mode == 3 && !e->tc_ok) return fail("t2s_decode: tcgen05 decode needs the TMA descriptor entry point");
+    e->st.decode_mode = mode;
+    if (mode == 1) {
       int grid = e->cd.attn_ctas;
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_persistent, NT, SMEM_MAX));
@@ -679,28 +730,31 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
       e->launches++;
     } else {
       // one graph = one decode step (122 kernel nodes); re-captured only when the context changes
-      if (e->decode_mode == 0 && (!e->graph_exec || memcmp(&e->graph_ctx, &e->cd, sizeof(Ctx)) != 0)) {
+      if (mode != 2 && (!e->graph_exec || e->graph_mode != mode || memcmp(&e->graph_ctx, &e->cd, sizeof(Ctx)) != 0)) {
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
         cudaStream_t cs;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         const long long before = e->launches;
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        launch_decode_step(e, e->cd, cs);
+        bool cap_ok = true;
+        if (mode == 3) cap_ok = launch_decode_step_tc(e, e->cd, cs);
+        else launch_decode_step(e, e->cd, cs);
         cudaGraph_t graph;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         e->nodes_per_step = (int)(e->launches - before);
         e->launches = before;
-        if (ce != cudaSuccess) { cudaStreamDestroy(cs); return fail("graph capture failed: %s", cudaGetErrorString(ce)); }
+        if (ce != cudaSuccess || !cap_ok) { cudaStreamDestroy(cs); return fail("graph capture failed: %s", cap_ok ? cudaGetErrorString(ce) : "tensor map encode"); }
         ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
         cudaGraphDestroy(graph);
         cudaStreamDestroy(cs);
         if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
         e->graph_ctx = e->cd;
+        e->graph_mode = mode;
       }
       int done_steps = 0;
       while (done_steps < budget && n_active > 0) {
         const int chunk = std::min(e->check_steps, budget - done_steps);
-        if (e->decode_mode == 2) {  // plain stream launches, no graph (profiling aid)
+        if (mode == 2) {  // plain stream launches, no graph (profiling aid)
           for (int i = 0; i < chunk; ++i) launch_decode_step(e, e->cd, s);
         } else {
           for (int i = 0; i < chunk; ++i) CK(cudaGraphLaunch(e->graph_exec, s));
@@ -851,7 +905,6 @@ extern "C" int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ct
 extern "C" int t2s_get_stats(t2s_engine* e, t2s_stats* out) {
   if (!e || !out) return fail("t2s_get_stats: null argument");
   e->st.kernel_launches = e->launches;
-  e->st.decode_mode = e->decode_mode;
   *out = e->st;
   return 0;
 }

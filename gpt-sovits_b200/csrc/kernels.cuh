@@ -271,6 +271,18 @@ __global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_
   if (threadIdx.x == 0) idx_out[b] = idx;
 }
 
+// Large-batch decode (tensor-core projections read their A operand through TMA, which cannot gather): put the
+// layer-0 input of every live row, written per slot by the sampler, in row order.
+__global__ void k_gather_x0(Ctx c, float* __restrict__ x0_rows, bf16* __restrict__ x0b_rows) {
+  const int r = blockIdx.x;
+  if (r >= ld_cg_i(c.n_rows)) return;
+  const int slot = ld_cg_i(c.row_slot + r);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    x0_rows[(size_t)r * D + d] = c.x0[(size_t)slot * D + d];
+    x0b_rows[(size_t)r * D + d] = c.x0b[(size_t)slot * D + d];
+  }
+}
+
 // ---- LayerNorm folding and the prefill -> decode hand-off ---------------------------------------------------
 // Wg[f][k] = W[f][k] * gamma[k] (bf16), c1[f] = sum_k Wg[f][k], c0[f] = bias[f] + sum_k W[f][k] * beta[k].
 // gamma == NULL: no LayerNorm in front of this matrix (layer-0 QKV): Wg = W, c1 = 0, c0 = bias.

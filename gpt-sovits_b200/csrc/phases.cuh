@@ -899,7 +899,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
   if (tid == 0) {
     *c.n_active = total;
     *c.n_rows = total;
-    *c.step = ld_cg_i(c.step) + 1;
+    if (n > 0) *c.step = ld_cg_i(c.step) + 1;  // graph modes replay whole chunks: steps after the last sequence retired do not count
     if (total > 0) { atomicAdd(c.stats + 1, 1ull); atomicAdd(c.stats + 2, (unsigned long long)total); }
   }
   // ---- split-KV work assignment for the next step's attention (valid for all layers)

@@ -149,10 +149,13 @@ int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* 
 
 enum {
   T2S_OPT_DECODE_MODE = 0,   /* 0: one kernel per phase, CUDA-graph replay; 1: persistent cooperative kernel;
-                                2: one kernel per phase, plain stream launches (profiling aid) */
+                                2: one kernel per phase, plain stream launches (profiling aid);
+                                3: CUDA graph with the projections on tcgen05 tensor cores (large batches);
+                                mode 1 switches to 3 by itself when batch >= T2S_OPT_TC_DECODE_MIN_BATCH */
   T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */
   T2S_OPT_NUM_CTAS = 2,      /* persistent grid size (0 = one CTA per SM) */
-  T2S_OPT_CHECK_STEPS = 3    /* graph mode: host checks the active count every this many steps */
+  T2S_OPT_CHECK_STEPS = 3,   /* graph mode: host checks the active count every this many steps */
+  T2S_OPT_TC_DECODE_MIN_BATCH = 4 /* batch size from which decode projections run on tcgen05 (default 160, the measured crossover; 0: never) */
 };
 int t2s_set_option(t2s_engine* e, int32_t option, int64_t value);
 

@@ -364,6 +364,43 @@ def test_prefill_tcgen05_gemm(engine, golden_dir, case, window):
     assert d <= LOGIT_TOL
 
 
+def test_large_batch_tcgen05_decode(engine):
+    """Large batches (default >= 160; forced to 64 here) switch the decode projections to the tcgen05 GEMMs (CUDA graph, mode 3).  Same teacher-forced
+    run with the persistent warp-MMA kernel (mode 1 forced): logits agree within the tolerance, and the
+    retirement bookkeeping (EOS forced at different steps) gives identical idx and tokens."""
+    from gpt_sovits_b200 import _lib
+    B, P, n = 72, 30, 10
+    L = synthetic.config_lens(B, 16, 48, seed=9)
+    ids, lens, prompt, bert = synthetic.make_inputs(B, L, P, seed=31)
+    ids = [t.cuda() for t in ids]
+    bert = [t.cuda() for t in bert]
+    prompt = prompt.cuda()
+    g = torch.Generator().manual_seed(3)
+    forced = torch.randint(0, 1024, (B, n), dtype=torch.int32, generator=g)
+    stop = torch.randint(3, n, (B,), generator=g)
+    for b in range(0, B, 3):
+        forced[b, int(stop[b])] = 1024  # every third utterance retires early
+    kw = dict(top_k=1, early_stop_num=n - 1, eos_suppress_steps=1, forced=forced, capture_logits=n)
+    try:
+        engine.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, 64)  # default crossover is 160
+        res_tc = engine.infer(ids, bert, prompt, **kw)
+        assert int(res_tc.stats["decode_mode"]) == 3
+        engine.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, 0)
+        res_pk = engine.infer(ids, bert, prompt, **kw)
+        assert int(res_pk.stats["decode_mode"]) == 1
+    finally:
+        engine.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, 160)
+    assert res_tc.idx == res_pk.idx
+    assert len(set(res_tc.idx)) > 3
+    a, b_ = res_tc.logits.cpu().numpy(), res_pk.logits.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b_))
+    d = float(np.nanmax(np.abs(a[:, :, :1024] - b_[:, :, :1024])))
+    print(f"tcgen05 decode (B={B}) vs persistent warp-MMA: max |dlogit| = {d:.4f}")
+    assert d <= LOGIT_TOL
+    assert torch.equal(res_tc.tokens, res_pk.tokens)
+    assert int(res_tc.stats["decode_steps"]) == int(res_pk.stats["decode_steps"]) == max(res_tc.idx)
+
+
 def test_drop_in_patch_with_fake_tts_caller(weights_seed0, pe_table):
     """The class-level patch, driven the way TTS.run drives the reference (TTS.py:1042-1047, 1210-1227,
     1259): instance-level rebinding to the batched variant, prompt as an .expand view, fp16 BERT
