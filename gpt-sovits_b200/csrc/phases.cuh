@@ -48,6 +48,7 @@ constexpr size_t SMEM_PROJ_MAX = ProjLayout<16>::BYTES;
 struct ProjArgs {
   const bf16* w;        // packed (gamma-folded) weights of this matrix
   int n_tiles;          // 16-feature tiles
+  int row_groups;       // > 1: units = tiles x row groups (phases with few tiles: more CTAs, less staging each)
   const bf16* in_b16;   // source rows [., K] bf16 (raw residual sums, or attention / FFN hidden)
   const int* in_idx;    // optional row gather (layer-0 input by slot, head rows after prefill)
   const float2* sp;     // partial row statistics of the source [., 32] -> LayerNorm folded in; NULL: no LN
@@ -148,7 +149,13 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
   const long long* kvoff = LY::kvoff(smem);
   const float2* st = LY::st(smem);
   const bool ln = a.sp != nullptr;
-  for (int nt = cta; nt < a.n_tiles; nt += ncta) {
+  // units = feature tiles x row groups; a row group is a multiple of 8 rows (one MMA n-tile)
+  const int rgn = (a.row_groups > 1) ? min(a.row_groups, (n_rows + 7) >> 3) : 1;
+  const int rows_pg = (((n_rows + rgn - 1) / rgn) + 7) & ~7;
+  for (int u = cta; u < a.n_tiles * rgn; u += ncta) {
+    const int nt = u % a.n_tiles, rg = u / a.n_tiles;
+    const int row_beg = rg * rows_pg, row_end = min(n_rows, row_beg + rows_pg);
+    if (row_beg >= row_end) continue;
     // this warp's KBW A fragments (k-blocks warp*KBW .. +KBW-1 of feature tile nt), loaded once per unit
     uint4 af[KBW];
     const uint4* wp = reinterpret_cast<const uint4*>(a.w) + ((size_t)nt * KB_ROW + warp * KBW) * 32 + lane;
@@ -160,11 +167,11 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
     const float c1 = ln ? a.c1[fme] : 0.f;
     const float resg = (OUT == OUT_O && a.res_g) ? a.res_g[fme] : 1.f;
     const float resb = (OUT == OUT_O && a.res_b) ? a.res_b[fme] : 0.f;
-    for (int r0 = 0; r0 < n_rows; r0 += RT) {
-      const int rows_here = min(RT, n_rows - r0);
+    for (int r0 = row_beg; r0 < row_end; r0 += RT) {
+      const int rows_here = min(RT, row_end - r0);
       const int n8 = (rows_here + 7) >> 3;
       __syncthreads();  // previous readers of xs / red / kvoff / st are done
-      proj_stage<OUT, KBW>(c, a, smem, r0, n_rows, nt);
+      proj_stage<OUT, KBW>(c, a, smem, r0, row_end, nt);
       __syncthreads();
       if (OUT == OUT_FFN1 && threadIdx.x < rows_here) {
         // duty of FFN1's unit nt: y2[:, 4nt..4nt+3] := LN1(y1) + b2 (FFN2 then adds its product; single writer)
@@ -282,7 +289,7 @@ __device__ __forceinline__ void phase_qkv(const Ctx& c, int layer, int n_rows, i
 __device__ __forceinline__ void phase_oproj(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_WO;
-  a.n_tiles = D / 16; a.layer = layer;
+  a.n_tiles = D / 16; a.layer = layer; a.row_groups = 4;
   a.in_b16 = c.attn;
   a.c0 = c.wvec + (size_t)layer * LV + VO_BO;
   if (layer > 0) {
@@ -306,7 +313,7 @@ __device__ __forceinline__ void phase_ffn1(const Ctx& c, int layer, int n_rows, 
 __device__ __forceinline__ void phase_ffn2(const Ctx& c, int layer, int n_rows, int cta, int ncta, unsigned char* sm) {
   ProjArgs a{};
   a.w = c.wmat + (size_t)layer * LW + OFF_W2;
-  a.n_tiles = D / 16; a.layer = layer;
+  a.n_tiles = D / 16; a.layer = layer; a.row_groups = 4;
   a.in_b16 = c.h;
   proj_phase<OUT_FFN2, 16>(c, a, n_rows, cta, ncta, sm);
 }

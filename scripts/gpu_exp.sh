@@ -1,7 +1,9 @@
 #!/bin/bash
-for v in T2S_EXP_VEC_LATE; do
-  cp gpt-sovits_b200/libt2s_$v.so gpt-sovits_b200/libt2s_b200.so
+cp gpt-sovits_b200/libt2s_b200.so /tmp/base.so
+for v in base acq; do
+  [ $v = acq ] && cp gpt-sovits_b200/libt2s_acq.so gpt-sovits_b200/libt2s_b200.so
   echo "=== $v"
-  python scripts/timeline.py --batch 1 --lo 80 --hi 80 --layers 1 2>&1 | grep -E "mean phase|step total|qkv L1" -A1 | grep -v "^--"
-  python scripts/timeline.py --batch 32 --layers 1 2>&1 | grep -E "mean phase|step total|qkv L1" -A1 | grep -v "^--"
+  python scripts/profile_step.py --barrier-bench --steps 1000 2>&1 | grep -E "148 CTAs, 10000|mode 1"
+  python scripts/profile_step.py --batch 1 --lo 80 --hi 80 --steps 500 | tail -1
 done
+cp /tmp/base.so gpt-sovits_b200/libt2s_b200.so
