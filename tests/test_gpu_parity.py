@@ -510,3 +510,88 @@ def test_full_size_properties(engine):
             row[seen] = np.where(row[seen] < 0, row[seen] * 1.35, row[seen] / 1.35)
             top2 = np.sort(row)[-2:]
             assert top2[1] - top2[0] <= LOGIT_TOL, f"utterance {b} diverged at step {s} with margin {top2[1]-top2[0]:.3f}"
+
+
+def test_edge_cases_small_and_limits(engine, weights_seed0, pe_table):
+    """Minimum sizes and parameter limits the reference's UIs can reach: one phoneme,
+    one prompt token; early_stop_num 0; the step cap; top_k above the vocabulary; temperature 0 (clamped to
+    1e-5, effectively greedy); top_p 0 (only the arg-max survives); repetition penalty off; EOS at step 0."""
+    from oracle.t2s_oracle import T2SOracle
+    o = T2SOracle(weights_seed0, pe_table)
+    idsc, lens, promptc, bertc = synthetic.make_inputs(2, [1, 3], 1, seed=40)
+    ids = [t.cuda() for t in idsc]
+    bert = [t.cuda() for t in bertc]
+    prompt = promptc.cuda()
+    # (a) tiny inputs against the oracle, teacher-forced
+    n = 4
+    out = o.generate([t.numpy() for t in idsc], [t.numpy() for t in bertc], promptc.numpy(), top_k=1,
+                     early_stop_num=n - 1, eos_window=1, record_logits=True)
+    forced = torch.tensor([out["generated"][b][:n] for b in range(2)], dtype=torch.int32)
+    res = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=n - 1, eos_suppress_steps=1, forced=forced,
+                       capture_logits=n)
+    got = res.logits.cpu().numpy()
+    worst = max(float(np.abs(got[s, :, :1024] - out["logits"][s][:, :1024]).max()) for s in range(n))
+    assert worst <= LOGIT_TOL, worst
+    assert res.idx == out["idx"]
+    # (b) early_stop_num = 0: stop at idx 0, only the prompt comes back (t2s_model.py:747)
+    r = engine.infer(ids, bert, prompt, top_k=5, early_stop_num=0, eos_suppress_steps=1)
+    assert r.idx == [0, 0] and all(s.shape[0] == 1 for s in r.sequences())
+    # (c) step cap: max_steps = 5 without early stop -> idx 4 (the reference's idx == 1499 rule, :747)
+    r = engine.infer(ids, bert, prompt, top_k=5, early_stop_num=-1, eos_suppress_steps=11, max_steps=5)
+    assert r.idx == [4, 4] and all(s.shape[0] == 1 + 4 for s in r.sequences())
+    # (d) top_k > vocab, temperature 0 -> clamp 1e-5 -> the sample is the arg-max of the penalised logits
+    r = engine.infer(ids, bert, prompt, top_k=5000, top_p=1.0, temperature=0.0, repetition_penalty=1.35,
+                     early_stop_num=5, eos_suppress_steps=1, capture_logits=6, seed=3)
+    lg = r.logits.cpu().numpy()
+    for b in range(2):
+        hist = list(map(int, promptc[b].numpy()))
+        for s in range(r.idx[b] + 1):
+            row = lg[s, b, : (1024 if s < 1 else 1025)].copy()
+            seen = np.unique(np.array(hist, dtype=np.int64))
+            row[seen] = np.where(row[seen] < 0, row[seen] * np.float32(1.35), row[seen] / np.float32(1.35))
+            top2 = np.sort(row)[-2:]
+            if top2[1] - top2[0] > 1e-3:
+                assert int(r.sampled[b, s]) == int(np.argmax(row)), (b, s)
+            hist.append(int(r.sampled[b, s]))
+    # (e) top_p = 0 keeps only the arg-max (utils.py:172-173: first sorted position always kept)
+    r = engine.infer(ids, bert, prompt, top_k=50, top_p=0.0, temperature=1.0, repetition_penalty=1.0,
+                     early_stop_num=4, eos_suppress_steps=1, capture_logits=5, seed=4)
+    lg = r.logits.cpu().numpy()
+    for b in range(2):
+        for s in range(r.idx[b] + 1):
+            row = lg[s, b, : (1024 if s < 1 else 1025)]
+            top2 = np.sort(row)[-2:]
+            if top2[1] - top2[0] > 1e-3:
+                assert int(r.sampled[b, s]) == int(np.argmax(row))  # penalty off: raw logits
+    # (f) EOS forced at step 1 for utterance 0 only: idx 1, one kept token; utterance 1 continues
+    forced = torch.tensor([[7, 1024, 0, 0], [8, 9, 10, 11]], dtype=torch.int32)
+    r = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=3, eos_suppress_steps=1, forced=forced)
+    assert r.idx == [1, 3]
+    assert r.sequences()[0].cpu().tolist() == [int(promptc[0, 0]), 7]
+    assert r.sequences()[1].cpu().tolist() == [int(promptc[1, 0]), 8, 9, 10]
+
+
+def test_argument_validation(engine):
+    """Error behaviour mirrors the reference where it has one (top_k <= 0 dies in torch.topk) and is explicit
+    elsewhere; every failure is a Python exception, never a silent fallback."""
+    ids, lens, prompt, bert = synthetic.make_inputs(2, [4, 6], 3, seed=41)
+    ids = [t.cuda() for t in ids]
+    bert = [t.cuda() for t in bert]
+    prompt = prompt.cuda()
+    with pytest.raises(RuntimeError, match="top_k"):
+        engine.infer(ids, bert, prompt, top_k=0)
+    with pytest.raises(ValueError):
+        engine.infer(ids, bert[:1], prompt)
+    with pytest.raises(ValueError):
+        engine.infer(ids, [bert[0], bert[1][:, :5]], prompt)
+    with pytest.raises(ValueError):
+        engine.infer(ids, [b.cpu() for b in bert], prompt)
+    with pytest.raises(ValueError):
+        engine.infer([], [], None)
+    with pytest.raises(RuntimeError, match="positional table"):
+        engine.infer(ids, bert, prompt, top_k=1, max_steps=5000)
+    with pytest.raises(RuntimeError, match="repetition_penalty"):
+        engine.infer(ids, bert, prompt, top_k=1, repetition_penalty=0.0)
+    # the engine is still usable after errors
+    r = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=2)
+    assert r.idx == [2, 2]
