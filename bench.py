@@ -302,6 +302,13 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         achieved = bytes_alg / (dec_ms / 1000.0) / 1e9  # rank 0's persistent decode kernel
+        traffic = None  # dram bytes of the same launch from the committed ncu --set full capture (profiles/)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("workload") == name and args.decode_mode == 1:
+                traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
+        except Exception:
+            pass
         h2d = sum(t.numel() * t.element_size() for t in ids_p) + sum(t.numel() * t.element_size() for t in bert_p) \
             + prompt_p.numel() * prompt_p.element_size()
         d2h = w["batch"] * (w["prompt"] + 1500) * 8 + w["batch"] * 4
@@ -318,7 +325,7 @@ def main():
             "roofline": {
                 "kernel": "k_decode_persistent" if args.decode_mode == 1 else "decode step graph (122 kernels)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_alg / args.steps,
                 "launch_ms": dec_ms / args.steps,
                 "decode_tokens_per_s_rank0": (toks / world) / (dec_ms / 1000.0),

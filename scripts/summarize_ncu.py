@@ -30,8 +30,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
         "launch__shared_mem_per_block_dynamic"]
-for rep, title in (("prof_decode_b32", "k_decode_persistent, B=32, 60 decode steps (mean KV ~ 280) — `ncu --set full --clock-control none`"),
-                   ("prof_prefill_b32", "prefill kernels (k_gemm_tc / k_prefill_attn), B=32 (7755 rows) — `ncu --set full`")):
+import json
+for rep, title in (("prof_decode_b32", "k_decode_persistent: the bench workload's decode launch (B=32, 1000 steps in ONE launch, mean KV 743) — `ncu --set full --clock-control none`"),
+                   ("prof_gemm_b32", "k_gemm_tc<128> (tcgen05/TMEM + TMA prefill projections), B=32 (7755 rows) — `ncu --set full`"),
+                   ("prof_pattn_b32", "k_prefill_attn (prefix-LM attention), B=32 — `ncu --set full`")):
     path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -47,5 +49,13 @@ for rep, title in (("prof_decode_b32", "k_decode_persistent, B=32, 60 decode ste
                 i = hdr.index(w)
                 out.append(f"| {w} | {r[i]} | {units[i]} |")
         out.append("")
+        if rep == "prof_decode_b32":
+            def val(nm):
+                i = hdr.index(nm); x = float(r[i].replace(",", "")); u = units[i].lower()
+                return x * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1, "tbyte": 1e12}.get(u, 1)
+            tr = {"kernel": name, "workload": "cfg2_b32", "decode_steps": 1000,
+                  "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                  "note": "one ncu --set full capture of the whole 1000-step persistent launch (profiler-time duration is not a bench number)"}
+            json.dump(tr, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:6000])
