@@ -38,6 +38,12 @@ constexpr int VO_BQKV = 0, VO_BO = 1536, VO_B1 = 2048, VO_B2 = 4096, VO_G1 = 460
               // LayerNorm folded into the consumer GEMMs (k_fold_ln): c1 = Wg 1, c0 = W beta + bias
               VO_C1_QKV = 6656, VO_C0_QKV = 8192, VO_C1_FFN1 = 9728, VO_C0_FFN1 = 11776, LV = 13824;
 
+// KV cache layout inside one layer's pool: [page][head][position in page][head dim] bf16, i.e. the K (or V) of one head
+// for one 64-position page is a contiguous 4 KB block (a TMA bulk copy can fetch it).  A row's `kvoff` is the element
+// offset of (its page, head 0, its position, dim 0); feature f = head*32 + dim lives kv_feat(f) elements further.
+__host__ __device__ constexpr long long kv_row_off(long long page, int pos_in_page) { return page * PAGE * D + (long long)pos_in_page * DH; }
+__host__ __device__ constexpr int kv_feat(int f) { return (f >> 5) * (PAGE * DH) + (f & (DH - 1)); }
+
 constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
 
 typedef __nv_bfloat16 bf16;
@@ -58,7 +64,7 @@ struct Ctx {
   float alpha_audio, alpha_text;
   int n_layer;
   int pe_len;
-  // KV cache: pools [n_layer][n_pages][PAGE][D] bf16, page table [B][max_pages]
+  // KV cache: pools [n_layer][n_pages][NH][PAGE][DH] bf16 (see kv_row_off), page table [B][max_pages]
   bf16* kpool;
   bf16* vpool;
   size_t kv_layer_stride;

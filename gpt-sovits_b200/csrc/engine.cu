@@ -13,6 +13,7 @@
 #include "../../include/t2s_b200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "cluster_decode.cuh"
 
 using namespace t2s;
 
@@ -64,6 +65,8 @@ struct t2s_engine {
   int device = 0, num_sms = 0;
   // weights
   DevBuf wmat, wvec, whead, wbert, bbert, emb_audio, emb_text, pe, wrow;  // wrow: row-major bf16 copies for the TMA GEMM
+  DevBuf wstream, hstream;  // cluster-stream decode: per-(layer, CTA rank) consumption-ordered weight streams
+  int max_clusters = 0;     // co-resident 16-CTA clusters of k_decode_cluster (0: unavailable)
   DevBuf wrow_g, wrow_head, wrow_head_g, head_c;  // gamma-folded row-major copies (Wqkv, W1 per layer; head) + head c1/c0
   bool weights_final = false;
   float alpha_audio = 1.f, alpha_text = 1.f;
@@ -150,6 +153,8 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   rc |= e->wrow_head.ensure((size_t)VPAD * D * 2);
   rc |= e->wrow_head_g.ensure((size_t)VPAD * D * 2);
   rc |= e->head_c.ensure((size_t)2 * VPAD * 4);
+  rc |= e->wstream.ensure((size_t)L * cs::C * cs::LAYER_BYTES);
+  rc |= e->hstream.ensure((size_t)cs::C * cs::HEAD_BYTES);
   rc |= e->x0b_slots.ensure((size_t)MAX_B * D * 2);
   rc |= e->logits.ensure((size_t)MAX_B * VPAD * 4);
   rc |= e->part.ensure((size_t)(MAX_B + 1024) * PART_STRIDE * 4);
@@ -179,6 +184,21 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   cudaFuncSetAttribute(k_bert_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
   cudaFuncSetAttribute(k_decode_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
   e->tc_ok = gemm_tc_init();
+  {
+    // cluster-stream decode kernel: 16-CTA clusters (non-portable size), ~200 KB dynamic shared memory per CTA
+    cudaError_t ce = cudaFuncSetAttribute(cs::k_decode_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cs::Smem));
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(cs::k_decode_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (ce == cudaSuccess) {
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(cs::C); lc.blockDim = dim3(cs::NTC); lc.dynamicSmemBytes = sizeof(cs::Smem);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs::C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      int mc = 0;
+      if (cudaOccupancyMaxActiveClusters(&mc, cs::k_decode_cluster, &lc) == cudaSuccess) e->max_clusters = mc;
+    }
+    cudaGetLastError();  // a failure here only disables decode mode 4
+  }
   e->prefill_gemm = e->tc_ok ? 1 : 0;  // tcgen05/TMEM + TMA GEMMs for prefill unless the driver entry point is missing
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -196,7 +216,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
-                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
+                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
@@ -334,7 +354,8 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
   k_fold_ln<<<(VPAD + 7) / 8, 256, 0, s>>>(e->wrow_head.as<bf16>(), vlast + VO_G2, vlast + VO_BE2, nullptr,
                                          e->wrow_head_g.as<bf16>(), e->head_c.as<float>(), e->head_c.as<float>() + VPAD, V, VPAD);
   k_pack_matrix<<<592, 256, 0, s>>>(e->whead.as<bf16>(), e->wrow_head_g.as<bf16>(), T2S_BF16, VPAD, D, VT);
-  e->launches += 2;
+  cs::k_pack_stream<<<1184, 256, 0, s>>>(e->wstream.as<unsigned char>(), e->hstream.as<bf16>(), e->wrow.as<bf16>(), e->wvec.as<float>(), e->wrow_head.as<bf16>(), L);
+  e->launches += 3;
   CK(cudaGetLastError());
   e->weights_final = true;
   return 0;
@@ -344,7 +365,7 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
 extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
-    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 3) return fail("decode mode must be 0, 1, 2 or 3"); e->decode_mode = (int)v; break;
+    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 4) return fail("decode mode must be 0 .. 4"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM:
       if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
       if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
@@ -528,7 +549,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
   std::vector<long long> kvoff(T);
   for (int r = 0; r < T; ++r)
-    kvoff[r] = ((long long)page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> 6)] * PAGE + (row_pos[r] & (PAGE - 1))) * D;
+    kvoff[r] = kv_row_off(page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> 6)], row_pos[r] & (PAGE - 1));
   CK(cudaMemcpyAsync(e->kvoff.p, kvoff.data(), (size_t)T * 8, cudaMemcpyHostToDevice, s));
   int* di = e->ints.as<int>();
   e->d_row_slot = di + o_row_slot; e->d_row_pos = di + o_row_pos; e->d_head_rows = di + o_head;
@@ -715,8 +736,29 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
     int mode = e->decode_mode;
     if (mode == 1 && e->tc_ok && e->tc_decode_min_batch > 0 && e->B >= e->tc_decode_min_batch) mode = 3;
     if (mode == 3 && !e->tc_ok) return fail("t2s_decode: tcgen05 decode needs the TMA descriptor entry point");
+    if (mode == 4) {
+      if (e->max_clusters < 1) return fail("t2s_decode: cluster-stream decode unavailable (no co-resident 16-CTA cluster)");
+      if (e->B > e->max_clusters * cs::RMAX) return fail("t2s_decode: cluster-stream decode holds at most %d sequences (got %d)", e->max_clusters * cs::RMAX, e->B);
+      if (e->cd.max_pages > 64) return fail("t2s_decode: cluster-stream decode supports at most 64 KV pages per sequence");
+    }
     e->st.decode_mode = mode;
-    if (mode == 1) {
+    if (mode == 4) {
+      const int ncl = std::min(e->max_clusters, e->B);
+      CK(cudaMemsetAsync(e->cd.bar, 0, 4, s));
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(ncl * cs::C); lc.blockDim = dim3(cs::NTC); lc.dynamicSmemBytes = sizeof(cs::Smem); lc.stream = s;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs::C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+      lc.attrs = at; lc.numAttrs = 2;
+      cudaError_t le = cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget);
+      if (le != cudaSuccess) {  // cooperative + cluster rejected: every CTA is co-resident anyway (grid <= max active clusters)
+        cudaGetLastError();
+        lc.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget));
+      }
+      e->launches++;
+    } else if (mode == 1) {
       int grid = e->cd.attn_ctas;
       int per_sm = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_persistent, NT, SMEM_MAX));

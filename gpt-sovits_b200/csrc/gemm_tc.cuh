@@ -224,7 +224,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           for (int j = 0; j < 4; ++j)
             o[j] = make_float4(x[4 * j] * QSCALE, x[4 * j + 1] * QSCALE, x[4 * j + 2] * QSCALE, x[4 * j + 3] * QSCALE);
         } else {
-          store_bf16x16((f0 < 2 * D ? ep.kpool + (f0 - D) : ep.vpool + (f0 - 2 * D)) + ep.layer_off + (size_t)kvo, x);
+          store_bf16x16((f0 < 2 * D ? ep.kpool + kv_feat(f0 - D) : ep.vpool + kv_feat(f0 - 2 * D)) + ep.layer_off + (size_t)kvo, x);
         }
       } else if (ep.mode == EPI_RESID) {
         const float4* r4 = reinterpret_cast<const float4*>(ep.resid + (size_t)row * N + f0);

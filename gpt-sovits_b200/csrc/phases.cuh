@@ -226,8 +226,8 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
               c.q[(size_t)r * D + f] = val * QSCALE;
             } else {
               const size_t off = (size_t)a.layer * c.kv_layer_stride + (size_t)kvoff[n];
-              if (f < 2 * D) c.kpool[off + (f - D)] = __float2bfloat16_rn(val);
-              else c.vpool[off + (f - 2 * D)] = __float2bfloat16_rn(val);
+              if (f < 2 * D) c.kpool[off + kv_feat(f - D)] = __float2bfloat16_rn(val);
+              else c.vpool[off + kv_feat(f - 2 * D)] = __float2bfloat16_rn(val);
             }
           }
         } else if (OUT == OUT_O) {
@@ -326,24 +326,6 @@ __device__ __forceinline__ void phase_head(const Ctx& c, int n_rows, int cta, in
   proj_phase<OUT_HEAD, 4>(c, a, n_rows, cta, ncta, sm);
 }
 
-// L2 prefetch of this CTA's K/V position ranges of `layer` (issued during the QKV phase, one grid barrier
-// before the attention phase reads them): one bulk-prefetch instruction per page run.
-__device__ __forceinline__ void prefetch_kv(const Ctx& c, int layer, int cta) {
-  const int tid = threadIdx.x;
-  const int e = tid >> 7, i = tid & 127;  // descriptor entry, page-run index
-  const int4 ds = __ldcg(reinterpret_cast<const int4*>(c.attn_desc) + cta * 2 + e);
-  if (ds.x < 0) return;
-  const int pbeg = ds.y, pend = ds.z, slot = ds.x >> 16;
-  const int p0 = (pbeg & ~(PAGE - 1)) + (i >> 1) * PAGE;  // page-aligned run start; even i: K, odd i: V
-  if (p0 >= pend) return;
-  const int a0 = max(p0, pbeg), a1 = min(p0 + PAGE, pend);
-  const int page = c.page_table[slot * c.max_pages + (a0 >> 6)];
-  const bf16* base = ((i & 1) ? c.vpool : c.kpool) + (size_t)layer * c.kv_layer_stride +
-                     ((size_t)page * PAGE + (a0 & (PAGE - 1))) * D;
-  const unsigned bytes = (unsigned)(a1 - a0) * D * 2;
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
-}
-
 // L2 prefetch of the weights this CTA will need in the phase AFTER the coming one (called right before a
 // grid barrier so HBM latency overlaps the barrier and the next phase).  `next` = the phase about to be
 // entered after the barrier is `cur + 1`; we prefetch for cur + 2's projection when cur + 1 has no weights.
@@ -365,8 +347,8 @@ __device__ __forceinline__ void prefetch_phase(const Ctx& c, int what, int layer
 // (split-KV); a CTA keeps an online-softmax state in registers while it stays on one sequence, the
 // partial states of a sequence are merged by the last CTA to finish it.
 //
-// Lane mapping: a K (or V) row is 1 KB = 64 x 16 B.  Lane l loads chunk l (head l/4, dims 8*(l%4)..+7)
-// and chunk 32+l (head 8+l/4): two fully coalesced 512 B requests per row per warp.
+// Lane mapping: lane l loads the 16-byte chunk (head l/4, dims 8*(l%4)..+7) and the one of head 8+l/4 of a position;
+// pages are head-major (kv_row_off), so a quad of lanes reads one 64 B head row.
 // =====================================================================================================
 struct AttnSmem {
   int pre[MAX_B + 1];
@@ -414,16 +396,17 @@ template <int U>
 __device__ __forceinline__ void attn_load(const bf16* kbase, const bf16* vbase, const int* pt, int p0, int pend, int lane,
                                           uint4 (&ka)[U], uint4 (&kb)[U], uint4 (&va)[U], uint4 (&vb)[U]) {
   const int page = pt[p0 >> 6];
-  const size_t rowoff = ((size_t)page * PAGE + (p0 & (PAGE - 1))) * D;
+  // lane l: 16-byte chunk of head l/4 (dims 8*(l%4)..+7) and of head 8 + l/4 (head-major pages, see kv_row_off)
+  const size_t rowoff = (size_t)kv_row_off(page, p0 & (PAGE - 1)) + (size_t)(lane >> 2) * (PAGE * DH) + (lane & 3) * 8;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (p0 + u < pend) {
-      const bf16* kr = kbase + rowoff + (size_t)u * D;
-      const bf16* vr = vbase + rowoff + (size_t)u * D;
-      ka[u] = ld_cg16(kr + lane * 8);
-      kb[u] = ld_cg16(kr + 256 + lane * 8);
-      va[u] = ld_cg16(vr + lane * 8);
-      vb[u] = ld_cg16(vr + 256 + lane * 8);
+      const bf16* kr = kbase + rowoff + (size_t)u * DH;
+      const bf16* vr = vbase + rowoff + (size_t)u * DH;
+      ka[u] = ld_cg16(kr);
+      kb[u] = ld_cg16(kr + 8 * PAGE * DH);
+      va[u] = ld_cg16(vr);
+      vb[u] = ld_cg16(vr + 8 * PAGE * DH);
     } else {
       ka[u] = kb[u] = va[u] = vb[u] = make_uint4(0, 0, 0, 0);
     }
@@ -584,6 +567,14 @@ __device__ void phase_attn_decode(const Ctx& c, int layer, int n_rows, int cta, 
 // =====================================================================================================
 constexpr int SV = 5;  // values per thread: 5*256 >= 1025
 
+// CTA-wide sync of the NT sampler threads: SB = 0 -> the whole CTA (__syncthreads); SB = 1 -> named barrier 1 over
+// the first NT threads (cluster-stream kernel: the CTA has an extra TMA producer warp that must not take part)
+template <int SB>
+__device__ __forceinline__ void cta_sync() {
+  if (SB == 0) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
 struct SampSmem {
   float redf[NW];
   int redi[NW];
@@ -612,6 +603,7 @@ __device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving fl
 }
 
 // block-wide (max value, smallest index among maxima)
+template <int SB>
 __device__ __forceinline__ int block_argmax(float v, int idx, SampSmem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -620,9 +612,9 @@ __device__ __forceinline__ int block_argmax(float v, int idx, SampSmem& sm) {
     const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
-  __syncthreads();
+  cta_sync<SB>();
   if (lane == 0) { sm.redf[warp] = v; sm.redi[warp] = idx; }
-  __syncthreads();
+  cta_sync<SB>();
   float bv = sm.redf[0];
   int bi = sm.redi[0];
 #pragma unroll
@@ -633,21 +625,23 @@ __device__ __forceinline__ int block_argmax(float v, int idx, SampSmem& sm) {
   }
   return bi;
 }
+template <int SB>
 __device__ __forceinline__ float block_max(float v, SampSmem& sm) {
   v = warp_max(v);
-  __syncthreads();
+  cta_sync<SB>();
   if ((threadIdx.x & 31) == 0) sm.redf[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync<SB>();
   float r = sm.redf[0];
 #pragma unroll
   for (int w = 1; w < NW; ++w) r = fmaxf(r, sm.redf[w]);
   return r;
 }
+template <int SB>
 __device__ __forceinline__ float block_sum(float v, SampSmem& sm) {  // fixed order => deterministic
   v = warp_sum(v);
-  __syncthreads();
+  cta_sync<SB>();
   if ((threadIdx.x & 31) == 0) sm.redf[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync<SB>();
   float r = 0.f;
 #pragma unroll
   for (int w = 0; w < NW; ++w) r += sm.redf[w];
@@ -655,19 +649,20 @@ __device__ __forceinline__ float block_sum(float v, SampSmem& sm) {  // fixed or
 }
 
 // k-th largest key among the thread-distributed values (8-bit radix select, 4 passes)
+template <int SB>
 __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV], const bool (&valid)[SV], int k,
                                                       SampSmem& sm) {
   uint32_t prefix = 0, mask = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    __syncthreads();
+    cta_sync<SB>();
     sm.hist[tid] = 0;  // NT == 256 bins
-    __syncthreads();
+    cta_sync<SB>();
 #pragma unroll
     for (int j = 0; j < SV; ++j)
       if (valid[j] && (key[j] & mask) == prefix) atomicAdd(&sm.hist[(key[j] >> shift) & 0xFFu], 1u);
-    __syncthreads();
+    cta_sync<SB>();
     if (warp == 0) {
       // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches k
       unsigned cnt[8], loc = 0;
@@ -689,7 +684,7 @@ __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV],
         }
       }
     }
-    __syncthreads();
+    cta_sync<SB>();
     prefix |= (uint32_t)sm.bcast[0] << shift;
     mask |= 0xFFu << shift;
     k = sm.bcast[1];
@@ -699,17 +694,18 @@ __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV],
 
 // top-p (rare path): full descending bitonic sort of (key, index), softmax over the sorted values,
 // inclusive prefix sum, remove where cum > top_p except the first (utils.py:169-179).
+template <int SB>
 __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, float top_p, SampSmem& sm) {
   const int tid = threadIdx.x;
   for (int i = tid; i < 2048; i += NT) sm.sortbuf[i] = 0ull;  // key 0 sorts last
-  __syncthreads();
+  cta_sync<SB>();
 #pragma unroll
   for (int j = 0; j < SV; ++j) {
     const int i = tid + NT * j;
     // ties: smaller index first in descending order (stable sort of -x) => store ~index in the low word
     if (valid[j]) sm.sortbuf[i] = ((unsigned long long)float_key(x[j]) << 32) | (uint32_t)(0xFFFFFFFFu - i);
   }
-  __syncthreads();
+  cta_sync<SB>();
   for (int size = 2; size <= 2048; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = tid; t < 1024; t += NT) {
@@ -719,7 +715,7 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
         const unsigned long long a = sm.sortbuf[lo], b = sm.sortbuf[hi];
         if ((a < b) == desc) { sm.sortbuf[lo] = b; sm.sortbuf[hi] = a; }
       }
-      __syncthreads();
+      cta_sync<SB>();
     }
   }
   // softmax over sorted values: max is element 0
@@ -733,16 +729,16 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
     e[j] = (i < width) ? expf(key_to_float((uint32_t)(sm.sortbuf[i] >> 32)) - mx) : 0.f;
     loc += e[j];
   }
-  const float total = block_sum(loc, sm);
+  const float total = block_sum<SB>(loc, sm);
   loc = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { e[j] = e[j] / total; loc += e[j]; }
-  __syncthreads();
+  cta_sync<SB>();
   sm.cum[tid] = loc;
-  __syncthreads();
+  cta_sync<SB>();
   float run = 0.f;
   for (int i = 0; i < tid; ++i) run += sm.cum[i];
-  __syncthreads();
+  cta_sync<SB>();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int i = 8 * tid + j;
@@ -750,11 +746,11 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
     // cum_probs > top_p is removed, position 0 always kept (utils.py:172-173); tag by clearing the key
     if ((i < width) && (i > 0) && (run > top_p)) sm.sortbuf[i] &= 0xFFFFFFFFull;
   }
-  __syncthreads();
+  cta_sync<SB>();
   // each thread looks for its own elements: build a removal bitmap in cum[] reinterpret (1025 bits)
   unsigned* bits = reinterpret_cast<unsigned*>(sm.cum);
   for (int i = tid; i < 64; i += NT) bits[i] = 0u;
-  __syncthreads();
+  cta_sync<SB>();
   for (int i = tid; i < width; i += NT) {
     const unsigned long long v = sm.sortbuf[i];
     if ((v >> 32) == 0) {
@@ -762,20 +758,20 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
       atomicOr(&bits[idx >> 5], 1u << (idx & 31));
     }
   }
-  __syncthreads();
+  cta_sync<SB>();
 #pragma unroll
   for (int j = 0; j < SV; ++j) {
     const int i = tid + NT * j;
     if (valid[j] && ((bits[i >> 5] >> (i & 31)) & 1u)) x[j] = -INFINITY;
   }
-  __syncthreads();
+  cta_sync<SB>();
 }
 
-__device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, SampSmem& sm) {
+template <int SB>
+__device__ void sample_row(const Ctx& c, int r, int step, SampSmem& sm) {
   const int tid = threadIdx.x;
-  const int step = ld_cg_i(c.step);
   const int width = (step < c.eos_window) ? (V - 1) : V;
-  for (int r = cta; r < n_active; r += ncta) {
+  {
     const int slot = ld_cg_i(c.active + r);
     float v[SV];
     bool valid[SV];
@@ -802,12 +798,12 @@ __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, Samp
       float bv = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll
       for (int j = 0; j < SV; ++j) if (valid[j] && (v[j] > bv)) { bv = v[j]; bi = tid + NT * j; }
-      greedy = block_argmax(bv, bi, sm);
+      greedy = block_argmax<SB>(bv, bi, sm);
     }
     float x[SV];
 #pragma unroll
     for (int j = 0; j < SV; ++j) x[j] = v[j];
-    if (c.top_p < 1.0f) block_top_p(x, valid, width, c.top_p, sm);
+    if (c.top_p < 1.0f) block_top_p<SB>(x, valid, width, c.top_p, sm);
     const float temp = fmaxf(c.temperature, 1e-5f);
 #pragma unroll
     for (int j = 0; j < SV; ++j) x[j] = x[j] / temp;
@@ -816,18 +812,18 @@ __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, Samp
       uint32_t key[SV];
 #pragma unroll
       for (int j = 0; j < SV; ++j) key[j] = float_key(x[j]);
-      const uint32_t pivot = block_kth_largest(key, valid, k, sm);
+      const uint32_t pivot = block_kth_largest<SB>(key, valid, k, sm);
 #pragma unroll
       for (int j = 0; j < SV; ++j) if (valid[j] && key[j] < pivot) x[j] = -INFINITY;
     }
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < SV; ++j) if (valid[j]) mx = fmaxf(mx, x[j]);
-    mx = block_max(mx, sm);
+    mx = block_max<SB>(mx, sm);
     float e[SV], loc = 0.f;
 #pragma unroll
     for (int j = 0; j < SV; ++j) { e[j] = valid[j] ? expf(x[j] - mx) : 0.f; loc += e[j]; }
-    const float total = block_sum(loc, sm);
+    const float total = block_sum<SB>(loc, sm);
     int tok;
     {
       float bv = -INFINITY; int bi = 0x7fffffff;
@@ -843,7 +839,7 @@ __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, Samp
         const float sc = (e[j] / total) / q;
         if (sc > bv) { bv = sc; bi = i; }
       }
-      tok = block_argmax(bv, bi, sm);
+      tok = block_argmax<SB>(bv, bi, sm);
     }
     // ---- bookkeeping (t2s_model.py:718-769)
     int emit = tok;
@@ -870,12 +866,18 @@ __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, Samp
         c.x0b[(size_t)slot * D + d] = __float2bfloat16_rn(xv);
       }
     }
-    __syncthreads();
+    cta_sync<SB>();
   }
+}
+
+__device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, SampSmem& sm) {
+  const int step = ld_cg_i(c.step);
+  for (int r = cta; r < n_active; r += ncta) sample_row<0>(c, r, step, sm);
 }
 
 // Retirement: compact the active list on device (no host round trip), publish next step's rows.
 // Runs on one CTA.  (t2s_model.py:724-745 does this with .tolist() + 48 index_selects.)
+template <int SB = 0>
 __device__ void phase_plan(const Ctx& c, int* smem_i) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = ld_cg_i(c.n_active);
@@ -888,7 +890,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     if (lane >= o) inc += v;
   }
   if (lane == 31) smem_i[warp] = inc;
-  __syncthreads();
+  cta_sync<SB>();
   int woff = 0, total = 0;
   for (int w = 0; w < NW; ++w) { if (w < warp) woff += smem_i[w]; total += smem_i[w]; }
   unsigned long long kvpos = 0;
@@ -898,7 +900,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     c.active[p] = slot;
     c.row_slot[p] = slot;
     c.row_pos[p] = pos;
-    c.row_kvoff[p] = ((long long)c.page_table[slot * c.max_pages + (pos >> 6)] * PAGE + (pos & (PAGE - 1))) * D;
+    c.row_kvoff[p] = kv_row_off(c.page_table[slot * c.max_pages + (pos >> 6)], pos & (PAGE - 1));
     c.seq_len[slot] = pos + 1;
     kvpos = (unsigned long long)(pos + 1);
   }
@@ -916,7 +918,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
   const int ncta = c.attn_ctas;
   int4* desc = reinterpret_cast<int4*>(c.attn_desc);
   for (int i = tid; i < 2 * ncta; i += NT) desc[i] = make_int4(-1, 0, 0, 0);
-  __syncthreads();
+  cta_sync<SB>();
   const int n2 = total;
   if (n2 == 0) return;
   if (n2 > ncta) {  // more rows than CTAs: whole rows, round-robin (n2 <= MAX_B < 2 * ncta)
@@ -927,9 +929,9 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
   int v = (tid < n2) ? np_s[tid] : 0, tot = v;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  __syncthreads();
+  cta_sync<SB>();
   if (lane == 0) smem_i[warp] = tot;
-  __syncthreads();
+  cta_sync<SB>();
   long long Np = 0;
   for (int w = 0; w < NW; ++w) Np += smem_i[w];
   // CTAs per row: 1 + share of the spare CTAs, capped by 16 partials and by the number of 8-position items
@@ -945,9 +947,9 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     int x = __shfl_up_sync(0xffffffffu, kin, o);
     if (lane >= o) kin += x;
   }
-  __syncthreads();
+  cta_sync<SB>();
   if (lane == 31) smem_i[warp] = kin;
-  __syncthreads();
+  cta_sync<SB>();
   int koff = 0;
   for (int w = 0; w < warp; ++w) koff += smem_i[w];
   const int c0 = koff + kin - k;  // first CTA of this row

@@ -66,6 +66,12 @@ __device__ __forceinline__ void consumer_cluster_sync(uint64_t* cbar, uint32_t& 
   parity ^= 1;
 }
 
+__device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+               : "memory");
+}
+
 struct Smem {
   unsigned char ring[STAGES][CHUNK];
   float gather[4][16][64];  // 4 exchange buffers, up to 16 peers x 64 floats
@@ -142,9 +148,63 @@ mb_stream(const unsigned char* __restrict__ w, const unsigned char* __restrict__
   cluster_arrive(); cluster_wait();
 }
 
+// sync-only: n exchanges of (16 B from each of 256 threads -> spread over the C peers) + wait.  mode 0: plain DSMEM stores +
+// bar.sync + remote mbarrier arrive.release + wait.acquire;  mode 1: st.async (data carries the completion) + wait
 template <int C>
-void run(int nclusters, int kvchunks, int do_sync, const unsigned char* w, const unsigned char* kv, float* out, int steps) {
-  const int n_layers = 24;
+__global__ void __launch_bounds__(256, 1) mb_sync(int n, int mode, float* out) {
+  __shared__ __align__(16) float buf[2][16][64];
+  __shared__ uint64_t cbar, ebar[2];
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(&cbar, C); mbar_init(&ebar[0], 1); mbar_init(&ebar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_arrive(); cluster_wait();
+  uint32_t cpar = 0, epar[2] = {0, 0};
+  float acc = 0.f;
+  const int peer = threadIdx.x >> 4, q = threadIdx.x & 15;  // 16 threads per peer (C=16: all 256 threads)
+  for (int i = 0; i < n; ++i) {
+    const int k = i & 1;
+    if (mode == 0) {
+      if (peer < C) st_cluster_f4(mapa(smem_u32(&buf[k][rank][q * 4]), peer), make_float4(acc, 1.f, 2.f, 3.f));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < C) mbar_arrive_remote(mapa(smem_u32(&cbar), threadIdx.x));
+      mbar_wait_cluster(&cbar, cpar); cpar ^= 1;
+    } else {
+      if (threadIdx.x == 0) mbar_expect_tx(&ebar[k], C * 16 * 16);
+      if (peer < C) st_async_f4(mapa(smem_u32(&buf[k][rank][q * 4]), peer), make_float4(acc, 1.f, 2.f, 3.f), mapa(smem_u32(&ebar[k]), peer));
+      mbar_wait_cluster(&ebar[k], epar[k]); epar[k] ^= 1;
+    }
+    acc += buf[k][threadIdx.x % C][q * 4];
+  }
+  if (acc == 1.2345f) out[0] = acc;
+  __syncwarp();
+  cluster_arrive(); cluster_wait();
+}
+template <int C>
+void run_sync(int nclusters, int mode, float* out) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * C); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (C > 8) CK(cudaFuncSetAttribute(mb_sync<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int n = 20000;
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernelEx(&cfg, mb_sync<C>, n, mode, out));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  printf("sync-only C=%2d clusters=%2d mode=%d (%s): %.0f ns per exchange\n", C, nclusters, mode, mode ? "st.async" : "st + arrive.release", best * 1e6 / n);
+}
+
+template <int C>
+void run(int nclusters, int kvchunks, int do_sync, const unsigned char* w, const unsigned char* kv, float* out, int steps, int n_layers = 24) {
   const int wchunks = 786432 * 8 / C / CHUNK;  // 24 (C=8) or 12 (C=16)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * C); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = sizeof(Smem);
@@ -170,8 +230,8 @@ void run(int nclusters, int kvchunks, int do_sync, const unsigned char* w, const
   const double bytes_cta = (double)n_layers * (wchunks + kvchunks) * CHUNK;
   const double ingest = bytes_cta * nclusters * C / (us_step * 1e-6) / 1e12;
   const double hbm = ((double)n_layers * wchunks * CHUNK * C + (double)n_layers * kvchunks * CHUNK * nclusters * C) / (us_step * 1e-6) / 1e12;
-  printf("C=%2d clusters=%2d (max %2d) kvchunks/layer/cta=%2d sync=%d : %8.1f us/step  per-SM %.1f GB/s  ingest %.2f TB/s  unique(HBM) %.2f TB/s\n",
-         C, nclusters, maxc, kvchunks, do_sync, us_step, bytes_cta / (us_step * 1e-6) / 1e9, ingest, hbm);
+  printf("L=%2d C=%2d clusters=%2d (max %2d) kvchunks/layer/cta=%2d sync=%d : %8.1f us/step  per-SM %.1f GB/s  ingest %.2f TB/s  unique(HBM) %.2f TB/s\n",
+         n_layers, C, nclusters, maxc, kvchunks, do_sync, us_step, bytes_cta / (us_step * 1e-6) / 1e9, ingest, hbm);
 }
 
 int main() {
@@ -180,28 +240,19 @@ int main() {
   unsigned char *w, *kv; float* out;
   CK(cudaMalloc(&w, wbytes)); CK(cudaMalloc(&kv, kvbytes)); CK(cudaMalloc(&out, 4096));
   CK(cudaMemset(w, 1, wbytes)); CK(cudaMemset(kv, 2, kvbytes));
+  for (int mode = 0; mode < 2; ++mode) { run_sync<8>(1, mode, out); run_sync<8>(15, mode, out); run_sync<16>(1, mode, out); run_sync<16>(7, mode, out); run_sync<4>(1, mode, out); }
   int dev_sms; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
   printf("SMs %d, smem/CTA %zu\n", dev_sms, sizeof(Smem));
   const int steps = 20;
   for (int sync = 0; sync <= 1; ++sync) {
-    run<8>(1, 0, sync, w, kv, out, steps);
     run<16>(1, 0, sync, w, kv, out, steps);
-    run<8>(8, 0, sync, w, kv, out, steps);
-    run<8>(16, 0, sync, w, kv, out, steps);
-    run<8>(18, 0, sync, w, kv, out, steps);
-    run<16>(4, 0, sync, w, kv, out, steps);
-    run<16>(8, 0, sync, w, kv, out, steps);
-    run<16>(9, 0, sync, w, kv, out, steps);
-    // + private KV traffic (B=32 at S~743: 1.2 GB/step = 390 KB/layer/cta over 128 CTAs = 12 chunks)
-    run<8>(16, 12, sync, w, kv, out, steps);
-    run<16>(8, 12, sync, w, kv, out, steps);
-    run<8>(16, 4, sync, w, kv, out, steps);
-    run<16>(8, 4, sync, w, kv, out, steps);
+    run<16>(1, 0, sync, w, kv, out, steps * 4, 6);   // 38 MB of weights: L2 resident after the first step
+    run<16>(7, 0, sync, w, kv, out, steps);
+    run<16>(7, 0, sync, w, kv, out, steps * 4, 6);
+    run<16>(7, 6, sync, w, kv, out, steps);           // + private KV (B=32 @ S~743: 1.2 GB/step/112 CTAs/24 layers = 14 chunks of 32K)
+    run<16>(7, 14, sync, w, kv, out, steps);
+    run<8>(15, 0, sync, w, kv, out, steps);
+    run<8>(15, 6, sync, w, kv, out, steps);
   }
-  // cluster size 4 / 2 for reference
-  run<4>(32, 0, 1, w, kv, out, steps);
-  run<4>(36, 0, 1, w, kv, out, steps);
-  run<2>(64, 0, 1, w, kv, out, steps);
-  run<2>(74, 0, 1, w, kv, out, steps);
   return 0;
 }

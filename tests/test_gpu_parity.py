@@ -72,7 +72,7 @@ def _compare_logits(res, g, eos_window, n_steps, slots_per_step=None):
     return worst, agree, total
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 4])
 def test_naive_b1_teacher_forced(engine, golden_dir, mode):
     """Config-1 shape (B=1, 80 phonemes + 150 prompt), reference infer_panel_naive goldens."""
     from gpt_sovits_b200 import _lib
@@ -109,7 +109,7 @@ def test_naive_b1_free_running(engine, golden_dir):
         assert top2[1] - top2[0] <= 2 * LOGIT_TOL, f"greedy diverged at step {first} with margin {top2[1]-top2[0]:.3f}"
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 4])
 def test_batch_b4_teacher_forced(engine, golden_dir, mode):
     """Ragged batch through infer_panel_batch_infer semantics (EOS column dropped at idx 0 only)."""
     from gpt_sovits_b200 import _lib
@@ -129,7 +129,7 @@ def test_batch_b4_teacher_forced(engine, golden_dir, mode):
         np.testing.assert_array_equal(res.sequences()[b].cpu().numpy(), g["y"][b])
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 4])
 def test_retirement_b6(golden_dir, pe_table, mode):
     """EOS-prone head: sequences retire at different steps (on-device compaction); outputs must come
     back in the original order with the reference's idx (t2s_model.py:724-745,779)."""
