@@ -4,24 +4,25 @@
 // (GPT_SoVITS/AR/models/t2s_model.py:701-769 / :878-914): 24 x T2SBlock.decode_next_token (:176-221), ar_predict_layer
 // (:706/:884), sample() (AR/models/utils.py:192) and the retirement bookkeeping (:720-763).
 //
-// Design (measured motivation in DESIGN.md section 4.4): a decode step is a chain of ~100 dependent tiny GEMVs; with
-// the layer split over all 148 SMs every link of the chain costs a grid barrier (~1.2 us) plus an L2 round trip.
-// Here a thread-block CLUSTER of C = 16 CTAs (one GPC) owns a few sequences end to end:
+// Design (measurements in DESIGN.md): a decode step is a chain of ~100 dependent tiny GEMVs; with a layer split over all
+// 148 SMs every link of the chain costs a grid barrier (~1.2 us) plus an L2 round trip.  Here a thread-block CLUSTER of
+// C = 16 CTAs (one GPC) owns a few sequences end to end:
 //   * CTA `rank` of a cluster is attention head `rank` and owns 1/16 of every weight matrix (32 q/k/v features, 32
 //     O-proj outputs, 128 FFN hidden units, 32 FFN2 outputs).  Its weights are ONE private, consumption-ordered byte
-//     stream (384 KB per layer, packed once by k_pack_stream) that a producer warp pulls through an 8 x 16 KB shared-
-//     memory ring with cp.async.bulk (TMA) + mbarriers, running ahead of the math and across step boundaries.
-//     Weights are stored in mma.m16n8k16 A-fragment order, so a consumer warp reads a fragment with one LDS.128.
+//     stream (393 KB per layer, packed once by k_pack_stream, mma.m16n8k16 A-fragment order, contiguous per warp).  A
+//     prefetch lane pulls the stream into L2 two layers ahead (cp.async.bulk.prefetch.L2); the consumer warps read their
+//     fragments straight from L2 into registers with 128-bit loads, 8 in flight per lane, the first batch of the next
+//     matrix issued BEFORE the hand-off wait that precedes it.  (Weights never touch shared memory: a TMA ring doubled
+//     the shared-memory traffic and bounded the GEMVs, see DESIGN.md.)
+//   * The K/V pages of the head (one contiguous 16 KB block per 128 positions: common.cuh kv_row_off) stream through an
+//     8 x 16 KB shared-memory ring fed by TMA bulk copies (one copy per page), running ahead across layers.
 //   * The four hand-offs of a layer (attention out, residual sum 1, FFN hidden, residual sum 2) are all-gathers through
 //     DISTRIBUTED SHARED MEMORY: st.async writes 16-byte pieces into every peer's buffer and completes bytes on the
 //     peer's mbarrier, so data and "ready" signal travel together (~0.3 us per hand-off instead of a grid barrier).
-//   * K/V of earlier positions are read straight from the paged bf16 cache by the head's CTA; the new position's k/v
-//     never leave the CTA before attention (they are also appended to the cache for later steps).
 //   * Logits go through global memory to one CTA per sequence, which runs the same fused sampler as the other modes
-//     (sample_row), then one grid barrier pair per STEP lets CTA 0 retire finished sequences and re-deal rows.
+//     (sample_row); one grid barrier pair per STEP lets CTA 0 retire finished sequences and re-deal rows.
 // All clusters read the same weight stream at about the same time, so HBM sees the weights once per step and the other
-// clusters hit L2 (126 MB); per-SM ingest measured at 150-170 GB/s, 17 TB/s aggregate over 7 clusters.
-// Everything is deterministic: fixed-order reductions, no floating-point atomics.
+// clusters hit L2 (126 MB).  Everything is deterministic: fixed-order reductions, no floating-point atomics.
 #pragma once
 #include "phases.cuh"
 
@@ -31,25 +32,27 @@ namespace cs {
 constexpr int C = 16;            // CTAs per cluster (= heads)
 constexpr int RMAX = 8;          // sequences per cluster (one MMA n-tile)
 constexpr int NCW = 8;           // consumer warps
-constexpr int NTC = (NCW + 1) * 32;  // + one TMA producer warp
-constexpr int SLOT = 16384;      // ring slot bytes
+constexpr int SLOT = 16384;      // K/V ring slot: one (page, head) block = K 8 KB | V 8 KB
 constexpr int NSLOT = 8;
+constexpr int NPW = 2;           // producer warps: K/V TMA ring; weight L2 prefetch + the layer-vector ring
+constexpr int NTC = (NCW + NPW) * 32;
 constexpr int HD = D / C;        // 32: q/k/v features, O-proj outputs, FFN2 outputs per CTA
 constexpr int FH = FF / C;       // 128 FFN hidden units per CTA
-// per-layer stream of one CTA: vectors 9,344 B | QKV 8 x 12 KB | [K/V pages of the cluster's sequences: from the cache,
-// not from this stream] | Wo 2 x 16 KB | W1 8 x 16 KB | W2 8 x 16 KB
-constexpr int CH_QKV = 12288, N_QKV = 8, CH_FULL = 16384, N_WO = 2, N_W1 = 8, N_W2 = 8;
 // vector chunk (fp32): biases of this CTA's slices, then the four LayerNorm vectors in full (every CTA normalises whole rows)
 constexpr int VC_BQ = 0, VC_BK = 32, VC_BV = 64, VC_BO = 96, VC_B1 = 128, VC_B2 = 256, VC_G1 = 288, VC_BE1 = VC_G1 + D,
               VC_G2 = VC_BE1 + D, VC_BE2 = VC_G2 + D, VC_FLOATS = VC_BE2 + D, CH_VEC = VC_FLOATS * 4;  // 9,344 B
-constexpr int OFFS_VEC = 0, OFFS_QKV = CH_VEC, OFFS_WO = OFFS_QKV + N_QKV * CH_QKV, OFFS_W1 = OFFS_WO + N_WO * CH_FULL,
-              OFFS_W2 = OFFS_W1 + N_W1 * CH_FULL, LAYER_BYTES = OFFS_W2 + N_W2 * CH_FULL;  // 402,560
-constexpr int KV_CHUNK_POS = 2 * PAGE;  // positions per K/V ring chunk: K page pair (8 KB) | V page pair (8 KB)
+// per-layer stream of one CTA: vectors | QKV (6 warps x 32 fragments) | Wo (8 x 8) | W1 (8 x 32) | W2 (8 x 32); a fragment
+// is 512 B (32 lanes x 16 B); inside a matrix the fragments of one warp are contiguous (the warp streams them in order)
+constexpr int NF_QKV = 32, NW_QKV = 6, NF_WO = 8, NF_W1 = 32, NF_W2 = 32;
+constexpr int SZ_QKV = NW_QKV * NF_QKV * 512, SZ_WO = NCW * NF_WO * 512, SZ_W1 = NCW * NF_W1 * 512, SZ_W2 = NCW * NF_W2 * 512;
+constexpr int OFFS_VEC = 0, OFFS_QKV = CH_VEC, OFFS_WO = OFFS_QKV + SZ_QKV, OFFS_W1 = OFFS_WO + SZ_WO, OFFS_W2 = OFFS_W1 + SZ_W1,
+              LAYER_BYTES = OFFS_W2 + SZ_W2;  // 402,560
 constexpr int HEAD_TILES = 5;    // 16-row tiles of ar_predict_layer per CTA (80 >= 65)
-constexpr int CH_HEAD = HEAD_TILES * 4 * 512, N_HEAD = 8, HEAD_BYTES = CH_HEAD * N_HEAD;  // 81,920
+constexpr int NF_HEAD = 32, HEAD_BYTES = HEAD_TILES * NF_HEAD * 512;  // 81,920
 constexpr int XS8 = D + 8;       // bf16 row stride of a 512-wide operand (bank-conflict-free B fragments)
 constexpr int HS8 = FF + 8;
 static_assert(LAYER_BYTES == (3 * D * D + D * D + 2 * FF * D) * 2 / C + CH_VEC && CH_VEC % 16 == 0, "stream size");
+static_assert(SLOT == KV_HEAD_STRIDE * 2, "one ring slot = one (page, head) K|V block");
 
 struct __align__(128) Smem {
   unsigned char ring[NSLOT][SLOT];
@@ -65,14 +68,15 @@ struct __align__(128) Smem {
   float red[NCW][16][RMAX + 1];
   unsigned char stage[RMAX * FH * 2]; // outgoing slice, bf16 [R][32] or [R][128]
   float am[NCW][RMAX], al[NCW][RMAX], aacc[NCW][RMAX][HD];
-  int pt[RMAX][64];                   // page-table rows of this cluster's sequences
+  int pt[RMAX][32];                   // page-table rows of this cluster's sequences (<= 32 pages of 128 positions)
   int row_slot[RMAX], row_pos[RMAX];
   long long row_kvoff[RMAX];
   alignas(16) float vec[2][VC_FLOATS];  // the layer's vectors (biases of the own slices, LayerNorm gamma / beta): 2-deep ring of its own
   unsigned long long full[NSLOT], empty[NSLOT], vfull[2], vempty[2], ebar[4], cbar;
   volatile int stop;
   volatile unsigned consumed, vconsumed;
-  volatile int step_seq;  // consumers -> producer: steps whose row descriptors (row_pos, pt, n_rows) are in place
+  volatile int step_seq;  // consumers -> producers: steps whose row descriptors (row_pos, pt, n_rows) are in place
+  volatile int unit_seq;  // consumers -> prefetch lane: (layer | head) units started so far
   volatile int n_rows;
 };
 
@@ -129,40 +133,38 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ---- weight stream layout (shared by the packer and the consumer) ---------------------------------------------------
-// Byte `off` of CTA `rank`'s layer stream -> (matrix id, source row, source column) of the bf16 element.
-// Inside a chunk: fragment (warp w, i) at (w*4 + i) * 512 B; inside a fragment lane*16 B + j*2 B in m16n8k16 A order:
+// Byte `off` (>= OFFS_QKV) of CTA `rank`'s layer stream -> (matrix id, source row, source column) of the bf16 element.
+// Inside a matrix: fragment (warp w, k) at (w*NF + k) * 512 B; inside a fragment lane*16 B + j*2 B in m16n8k16 A order:
 // lane = g*4+t holds rows g | g+8, cols 2t,2t+1 | +8:  j = 0,1:(g,2t..) 2,3:(g+8,2t..) 4,5:(g,2t+8..) 6,7:(g+8,2t+8..)
-__host__ __device__ inline void stream_src(int off, int rank, int& mat, int& row, int& col) {
-  int c, rel;  // chunk, byte inside the chunk (callers handle off < OFFS_QKV: the vector chunk)
-  if (off < OFFS_WO) { mat = 0; c = (off - OFFS_QKV) / CH_QKV; rel = (off - OFFS_QKV) % CH_QKV; }
-  else if (off < OFFS_W1) { mat = 1; c = (off - OFFS_WO) / CH_FULL; rel = (off - OFFS_WO) % CH_FULL; }
-  else if (off < OFFS_W2) { mat = 2; c = (off - OFFS_W1) / CH_FULL; rel = (off - OFFS_W1) % CH_FULL; }
-  else { mat = 3; c = (off - OFFS_W2) / CH_FULL; rel = (off - OFFS_W2) % CH_FULL; }
-  const int frag = rel >> 9, w = frag >> 2, i = frag & 3;
+__host__ __device__ inline void frag_elem(int rel, int nf, int& w, int& k, int& fr, int& kc) {
+  const int frag = rel >> 9;
+  w = frag / nf; k = frag % nf;
   const int lane = (rel >> 4) & 31, j = (rel >> 1) & 7;
   const int g = lane >> 2, t = lane & 3;
-  const int fr = g + ((j & 2) ? 8 : 0);                       // row inside the 16-feature tile
-  const int kc = 2 * t + (j & 1) + ((j & 4) ? 8 : 0);         // column inside the 16-wide k-block
-  int tile_row0, kb;
-  if (mat == 0) {         // warp w < 6: tile w = (q|k|v = w>>1, half = w&1) of head `rank`; k-blocks 4c..4c+3
-    tile_row0 = (w >> 1) * D + rank * HD + (w & 1) * 16; kb = 4 * c + i;
-  } else if (mat == 1) {  // Wo: tile w&1 of the 32 outputs, K quarter w>>1 (8 k-blocks), chunk c = half of it
-    tile_row0 = rank * HD + (w & 1) * 16; kb = (w >> 1) * 8 + 4 * c + i;
-  } else if (mat == 2) {  // W1: tile w of the 128 hidden units
-    tile_row0 = rank * FH + w * 16; kb = 4 * c + i;
-  } else {                // W2: tile w&1 of the 32 outputs, K quarter w>>1 (32 k-blocks)
-    tile_row0 = rank * HD + (w & 1) * 16; kb = (w >> 1) * 32 + 4 * c + i;
-  }
-  row = tile_row0 + fr; col = kb * 16 + kc;
+  fr = g + ((j & 2) ? 8 : 0);                    // row inside the 16-feature tile
+  kc = 2 * t + (j & 1) + ((j & 4) ? 8 : 0);      // column inside the 16-wide k-block
 }
-// head stream: chunk c, warp w < HEAD_TILES: vocabulary tile (rank + 16 w), k-blocks 4c..4c+3
+__host__ __device__ inline void stream_src(int off, int rank, int& mat, int& row, int& col) {
+  int w, k, fr, kc;
+  if (off < OFFS_WO) {         // QKV: warp w < 6 = tile (q|k|v = w>>1, half = w&1) of head `rank`, k-block k
+    mat = 0; frag_elem(off - OFFS_QKV, NF_QKV, w, k, fr, kc);
+    row = (w >> 1) * D + rank * HD + (w & 1) * 16 + fr; col = k * 16 + kc;
+  } else if (off < OFFS_W1) {  // Wo: tile w&1 of the 32 outputs, K quarter w>>1 (8 k-blocks)
+    mat = 1; frag_elem(off - OFFS_WO, NF_WO, w, k, fr, kc);
+    row = rank * HD + (w & 1) * 16 + fr; col = ((w >> 1) * 8 + k) * 16 + kc;
+  } else if (off < OFFS_W2) {  // W1: tile w of the 128 hidden units
+    mat = 2; frag_elem(off - OFFS_W1, NF_W1, w, k, fr, kc);
+    row = rank * FH + w * 16 + fr; col = k * 16 + kc;
+  } else {                     // W2: tile w&1 of the 32 outputs, K quarter w>>1 (32 k-blocks)
+    mat = 3; frag_elem(off - OFFS_W2, NF_W2, w, k, fr, kc);
+    row = rank * HD + (w & 1) * 16 + fr; col = ((w >> 1) * 32 + k) * 16 + kc;
+  }
+}
+// head stream: warp w < HEAD_TILES: vocabulary tile (rank + 16 w), k-block k
 __host__ __device__ inline void head_src(int off, int rank, int& row, int& col) {
-  const int c = off / CH_HEAD, rel = off % CH_HEAD;
-  const int frag = rel >> 9, w = frag >> 2, i = frag & 3;
-  const int lane = (rel >> 4) & 31, j = (rel >> 1) & 7;
-  const int g = lane >> 2, t = lane & 3;
-  row = (rank + C * w) * 16 + g + ((j & 2) ? 8 : 0);
-  col = (4 * c + i) * 16 + 2 * t + (j & 1) + ((j & 4) ? 8 : 0);
+  int w, k, fr, kc;
+  frag_elem(off, NF_HEAD, w, k, fr, kc);
+  row = (rank + C * w) * 16 + fr; col = k * 16 + kc;
 }
 
 // wrow: row-major bf16 layer matrices [n_layer][LW] (OFF_* offsets); wvec: [n_layer][LV] fp32; whead_row: [V][D] bf16
@@ -211,23 +213,26 @@ __global__ void k_pack_stream(unsigned char* __restrict__ wstream, bf16* __restr
 }
 
 // ---- consumer-side building blocks -------------------------------------------------------------------------------------
-__device__ __forceinline__ bool mbar_test(void* b, uint32_t parity) {  // non-blocking probe
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ unsigned ring_slot(unsigned i) { return i & (NSLOT - 1); }
 __device__ __forceinline__ unsigned ring_par(unsigned i) { return (i >> 3) & 1u; }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-// One matrix = NCH ring chunks.  Every consumer warp w < NWA takes fragments [4w, 4w+4) of each chunk and multiplies them
-// with the activation rows `act` (bf16, row stride `astride` elements) at k-blocks kb0 + 4c + i.  acc = 16 features x
-// 8 sequences in the m16n8k16 C layout (c0,c1: feature g, sequences 2t,2t+1; c2,c3: feature g+8).
-// All NCH "full" barriers are probed once up front (one lane each); chunks that had already landed need no further wait,
-// and the fragments of chunk c+1 are fetched from shared memory while the MMAs of chunk c issue.
-template <int NCH, int NWA>
-__device__ __forceinline__ void gemv_stream(Smem& sm, unsigned& cons, const bf16* act, int astride, int kb0, float (&acc)[4]) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Weight fragments come straight from L2 (prefetched there two layers ahead): 8 x 128-bit loads in flight per lane.
+constexpr int FB = 8;  // fragments per batch
+__device__ __forceinline__ void ldg_batch(const uint4* p, uint4 (&f)[FB]) {  // p = warp's fragment base + lane
+#pragma unroll
+  for (int i = 0; i < FB; ++i) f[i] = ld_weight16(p + i * 32);
+}
+// One matrix slice of this warp = NF fragments (k-blocks kb0 .. kb0+NF-1 of one 16-feature tile), `first` = its first batch
+// (already in flight / landed).  acc = 16 features x 8 sequences in the m16n8k16 C layout (c0,c1: feature g, sequences
+// 2t,2t+1; c2,c3: feature g+8).  act: bf16 activation rows (row stride astride elements).
+template <int NF>
+__device__ __forceinline__ void gemv_ldg(const uint4* wp, uint4 (&first)[FB], const bf16* act, int astride, int kb0, float (&acc)[4]) {
+  const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float a[4][4];
 #pragma unroll
@@ -235,37 +240,20 @@ __device__ __forceinline__ void gemv_stream(Smem& sm, unsigned& cons, const bf16
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
   const bf16* arow = act + (size_t)g * astride + kb0 * 16;
-  const unsigned base = cons;
-  bool rdy = true;
-  if (lane < NCH) rdy = mbar_test(&sm.full[ring_slot(base + lane)], ring_par(base + lane));
-  const unsigned ready = __ballot_sync(0xffffffffu, rdy);
-  uint4 f[4], fn[4];
-  auto fetch = [&](int c, uint4 (&dst)[4]) {
-    const unsigned slot = ring_slot(base + c);
-    if (!((ready >> c) & 1u)) mbar_wait(&sm.full[slot], ring_par(base + c));
-    if (warp < NWA) {
-      const uint4* fp = reinterpret_cast<const uint4*>(sm.ring[slot]) + (warp * 4) * 32 + lane;
+  uint4 nxt[FB];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = fp[i * 32];
+  for (int b = 0; b < NF / FB; ++b) {
+    if (b + 1 < NF / FB) ldg_batch(wp + (b + 1) * FB * 32, nxt);
+#pragma unroll
+    for (int i = 0; i < FB; ++i) {
+      const uint32_t* xr = reinterpret_cast<const uint32_t*>(arow + (b * FB + i) * 16);
+      mma_bf16_16816(a[i & 3], first[i], xr[t], xr[4 + t]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[slot]);
-  };
-  fetch(0, f);
+    if (b + 1 < NF / FB) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if (c + 1 < NCH) fetch(c + 1, fn);
-    if (warp < NWA) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t* xr = reinterpret_cast<const uint32_t*>(arow + (4 * c + i) * 16);
-        mma_bf16_16816(a[i], f[i], xr[t], xr[4 + t]);
-      }
+      for (int i = 0; i < FB; ++i) first[i] = nxt[i];
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f[i] = fn[i];
   }
-  cons = base + NCH;
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = (a[0][j] + a[1][j]) + (a[2][j] + a[3][j]);
 }
@@ -283,7 +271,6 @@ __device__ __forceinline__ void all_gather(Smem& sm, uint32_t dst, int dst_strid
 }
 
 // LayerNorm of the gathered residual rows (e24 + st24) -> xn (bf16, all features) and xres (fp32, own slice from yown).
-// gam / bet: the layer's vectors inside the held ring slot (shared memory).
 __device__ __forceinline__ void layer_norm_rows(Smem& sm, int R, uint32_t rank, const float* gam, const float* bet) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < R) {
@@ -338,9 +325,18 @@ __device__ __forceinline__ void residual_epilogue(Smem& sm, const float (&acc)[4
 }
 
 // Single-query attention of head `rank` for the cluster's R sequences.  The cached positions [0, pos) arrive through the
-// ring as chunks of up to 128 positions: K rows at byte i*64, V rows at 8192 + i*64 (head-major pages are contiguous).
-// Position `pos` (this step's token) comes from shared memory.  Warp w takes positions 16w..16w+15 of a chunk; a quad of
-// lanes owns one position (4 x 16 B = the head's 32 dims) and keeps an online-softmax state; quads, then warps are merged.
+// ring, one 128-position page per slot: K rows at byte i*64, V rows at 8192 + i*64.  Position `pos` (this step's token)
+// comes from shared memory.  Warp w takes positions 16w..16w+15 of a page; a quad of lanes owns two of them (4 x 16 B =
+// the head's 32 dims each), scores both, then folds them into its online-softmax state in one update; quads, then warps
+// are merged in a fixed order.
+__device__ __forceinline__ float dot8(const float (&q)[8], const uint4& k) {
+  return q[0] * bf_lo(k.x) + q[1] * bf_hi(k.x) + q[2] * bf_lo(k.y) + q[3] * bf_hi(k.y) + q[4] * bf_lo(k.z) + q[5] * bf_hi(k.z) +
+         q[6] * bf_lo(k.w) + q[7] * bf_hi(k.w);
+}
+__device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) {
+  acc[0] += p * bf_lo(v.x); acc[1] += p * bf_hi(v.x); acc[2] += p * bf_lo(v.y); acc[3] += p * bf_hi(v.y);
+  acc[4] += p * bf_lo(v.z); acc[5] += p * bf_hi(v.z); acc[6] += p * bf_lo(v.w); acc[7] += p * bf_hi(v.w);
+}
 __device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quad = lane >> 2, part = lane & 3;
@@ -352,53 +348,51 @@ __device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R) 
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    auto visit = [&](const uint4& kk, const uint4& vv, bool ok) {
-      float s = qv[0] * bf_lo(kk.x) + qv[1] * bf_hi(kk.x) + qv[2] * bf_lo(kk.y) + qv[3] * bf_hi(kk.y) +
-                qv[4] * bf_lo(kk.z) + qv[5] * bf_hi(kk.z) + qv[6] * bf_lo(kk.w) + qv[7] * bf_hi(kk.w);
+    {  // this step's token: warp 0, quad 0
+      const uint4 kk = *reinterpret_cast<const uint4*>(&sm.knew[n][part * 8]);
+      float s = dot8(qv, kk);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (ok) {
-        const float mn = fmaxf(m, s);
-        const float corr = exp2f(m - mn), p = exp2f(s - mn);
-        m = mn;
-        l = l * corr + p;
-        acc[0] = acc[0] * corr + p * bf_lo(vv.x); acc[1] = acc[1] * corr + p * bf_hi(vv.x);
-        acc[2] = acc[2] * corr + p * bf_lo(vv.y); acc[3] = acc[3] * corr + p * bf_hi(vv.y);
-        acc[4] = acc[4] * corr + p * bf_lo(vv.z); acc[5] = acc[5] * corr + p * bf_hi(vv.z);
-        acc[6] = acc[6] * corr + p * bf_lo(vv.w); acc[7] = acc[7] * corr + p * bf_hi(vv.w);
+      if (warp == 0 && quad == 0) {
+        m = s; l = 1.f;
+        axpy8(acc, 1.f, *reinterpret_cast<const uint4*>(&sm.vnew[n][part * 8]));
       }
-    };
-    // this step's token: warp 0, quad 0
-    visit(*reinterpret_cast<const uint4*>(&sm.knew[n][part * 8]), *reinterpret_cast<const uint4*>(&sm.vnew[n][part * 8]),
-          warp == 0 && quad == 0);
-    for (int p0 = 0; p0 < pos; p0 += KV_CHUNK_POS) {
-      const int np = min(KV_CHUNK_POS, pos - p0);
+    }
+    for (int p0 = 0; p0 < pos; p0 += PAGE) {
+      const int np = min(PAGE, pos - p0);
       const unsigned slot = ring_slot(cons);
       mbar_wait(&sm.full[slot], ring_par(cons));
       const unsigned char* kb = sm.ring[slot] + part * 16;
-      uint4 kk[2], vv[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = warp * 16 + u * 8 + quad;
-        if (i < np) {
-          kk[u] = *reinterpret_cast<const uint4*>(kb + i * 64);
-          vv[u] = *reinterpret_cast<const uint4*>(kb + 8192 + i * 64);
-        } else {
-          kk[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0);
-        }
-      }
+      const int i0 = warp * 16 + quad, i1 = i0 + 8;
+      const bool ok0 = i0 < np, ok1 = i1 < np;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      const uint4 k0 = ok0 ? *reinterpret_cast<const uint4*>(kb + i0 * 64) : z;
+      const uint4 k1 = ok1 ? *reinterpret_cast<const uint4*>(kb + i1 * 64) : z;
+      const uint4 v0 = ok0 ? *reinterpret_cast<const uint4*>(kb + 8192 + i0 * 64) : z;
+      const uint4 v1 = ok1 ? *reinterpret_cast<const uint4*>(kb + 8192 + i1 * 64) : z;
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[slot]);
       ++cons;
+      float s0 = dot8(qv, k0), s1 = dot8(qv, k1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (ok0) {  // ok1 implies ok0
+        const float mn = fmaxf(m, ok1 ? fmaxf(s0, s1) : s0);
+        const float corr = fast_exp2(m - mn), e0 = fast_exp2(s0 - mn), e1 = ok1 ? fast_exp2(s1 - mn) : 0.f;
+        m = mn;
+        l = l * corr + e0 + e1;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) visit(kk[u], vv[u], warp * 16 + u * 8 + quad < np);
+        for (int j = 0; j < 8; ++j) acc[j] *= corr;
+        axpy8(acc, e0, v0);
+        axpy8(acc, e1, v1);
+      }
     }
     // merge the 8 quads of the warp (fixed xor tree: deterministic)
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
       const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
       const float mn = fmaxf(m, mo);
-      const float ca = (m == -INFINITY) ? 0.f : exp2f(m - mn), cb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+      const float ca = (m == -INFINITY) ? 0.f : fast_exp2(m - mn), cb = (mo == -INFINITY) ? 0.f : fast_exp2(mo - mn);
       l = l * ca + lo * cb;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -424,7 +418,7 @@ __device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R) 
 #pragma unroll
       for (int w = 0; w < NCW; ++w) {
         const float mw = sm.am[w][n];
-        const float sc = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+        const float sc = (mw == -INFINITY) ? 0.f : fast_exp2(mw - M);
         L += sm.al[w][n] * sc;
         A += sm.aacc[w][n][d] * sc;
       }
@@ -459,6 +453,10 @@ struct GridBar {
   }
 };
 
+__device__ __forceinline__ void l2_prefetch(const unsigned char* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // =====================================================================================================================
 __global__ void __launch_bounds__(NTC, 1)
 k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigned char* __restrict__ hstream, int max_new_steps) {
@@ -471,78 +469,67 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
     for (int k = 0; k < 4; ++k) mbar_init(&sm.ebar[k], 1);
     for (int k = 0; k < 2; ++k) { mbar_init(&sm.vfull[k], 1); mbar_init(&sm.vempty[k], NCW); }
     mbar_init(&sm.cbar, C);
-    sm.stop = 0; sm.consumed = 0; sm.vconsumed = 0; sm.step_seq = 0; sm.n_rows = 0;
+    sm.stop = 0; sm.consumed = 0; sm.vconsumed = 0; sm.step_seq = 0; sm.unit_seq = 0; sm.n_rows = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   cluster_sync_all();
+  const int units_per_step = c.n_layer + 1;  // 24 layers + the head
 
   if (warp == NCW) {
-    // ---------------- producer: this CTA's byte stream (weights + the K/V pages of its head) through the ring ------------
+    // ---------------- producer 1: the K/V pages of head `rank` of this cluster's sequences, through the ring --------------
     if (lane == 0) {
-      unsigned issued = 0, vissued = 0;
+      unsigned issued = 0;
       int steps_done = 0;
       bool run = true;
-      auto acquire = [&]() -> bool {  // wait for the next ring slot to be free (or for the stop flag)
-        const unsigned slot = ring_slot(issued), par = ring_par(issued) ^ 1u;
-        while (!mbar_try(&sm.empty[slot], par)) { if (sm.stop) return false; }
-        return true;
-      };
-      auto push = [&](const unsigned char* src, uint32_t bytes) -> bool {
-        if (!acquire()) return false;
-        const unsigned slot = ring_slot(issued);
-        mbar_expect_tx(&sm.full[slot], bytes);
-        bulk_load(sm.ring[slot], src, bytes, &sm.full[slot]);
-        ++issued;
-        return true;
-      };
       while (run) {
+        while (sm.step_seq <= steps_done) { if (sm.stop) { run = false; break; } }  // rows of the step known?
+        if (!run) break;
+        asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows appended by generic-proxy stores in earlier steps
+        const int R = sm.n_rows;
         for (int layer = 0; layer < c.n_layer && run; ++layer) {
-          const unsigned char* base = wstream + ((size_t)layer * C + rank) * LAYER_BYTES;
-          {  // the layer's vectors go to their own 2-deep ring (they are needed during the whole layer)
-            const unsigned vs = vissued & 1u, vp = ((vissued >> 1) & 1u) ^ 1u;
-            while (!mbar_try(&sm.vempty[vs], vp)) { if (sm.stop) { run = false; break; } }
-            if (!run) break;
-            mbar_expect_tx(&sm.vfull[vs], CH_VEC);
-            bulk_load(sm.vec[vs], base + OFFS_VEC, CH_VEC, &sm.vfull[vs]);
-            ++vissued;
-          }
-          for (int ch = 0; ch < N_QKV && run; ++ch) run = push(base + OFFS_QKV + ch * CH_QKV, CH_QKV);
-          if (!run) break;
-          if (layer == 0) {  // the K/V list of a step is known once the consumers have read the plan
-            while (sm.step_seq <= steps_done) { if (sm.stop) { run = false; break; } }
-            if (!run) break;
-            asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows appended by generic-proxy stores in earlier steps
-          }
-          const int R = sm.n_rows;
-          const bf16* kl = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * (PAGE * DH);
-          const bf16* vl = c.vpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * (PAGE * DH);
+          const bf16* kl = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE;
           for (int n = 0; n < R && run; ++n) {
             const int pos = sm.row_pos[n];
-            for (int p0 = 0; p0 < pos && run; p0 += KV_CHUNK_POS) {
-              if (!(run = acquire())) break;
-              const unsigned slot = ring_slot(issued);
-              const int n0 = min(PAGE, pos - p0), n1 = min(PAGE, max(pos - p0 - PAGE, 0));
-              mbar_expect_tx(&sm.full[slot], (uint32_t)(n0 + n1) * (2 * DH * 2));
-              const size_t o0 = (size_t)sm.pt[n][p0 >> 6] * (PAGE * D);
-              bulk_load(sm.ring[slot], kl + o0, n0 * DH * 2, &sm.full[slot]);
-              bulk_load(sm.ring[slot] + 8192, vl + o0, n0 * DH * 2, &sm.full[slot]);
-              if (n1 > 0) {
-                const size_t o1 = (size_t)sm.pt[n][(p0 >> 6) + 1] * (PAGE * D);
-                bulk_load(sm.ring[slot] + 4096, kl + o1, n1 * DH * 2, &sm.full[slot]);
-                bulk_load(sm.ring[slot] + 8192 + 4096, vl + o1, n1 * DH * 2, &sm.full[slot]);
-              }
+            for (int p0 = 0; p0 < pos; p0 += PAGE) {
+              const unsigned slot = ring_slot(issued), par = ring_par(issued) ^ 1u;
+              while (!mbar_try(&sm.empty[slot], par)) { if (sm.stop) { run = false; break; } }
+              if (!run) break;
+              const uint32_t bytes = (uint32_t)(PAGE * DH * 2 + min(PAGE, pos - p0) * DH * 2);  // K block + the valid V rows
+              mbar_expect_tx(&sm.full[slot], bytes);
+              bulk_load(sm.ring[slot], kl + (size_t)sm.pt[n][p0 >> PAGE_SHIFT] * KV_PAGE_STRIDE, bytes, &sm.full[slot]);
               ++issued;
             }
           }
-          for (int ch = 0; ch < N_WO + N_W1 + N_W2 && run; ++ch) run = push(base + OFFS_WO + ch * CH_FULL, CH_FULL);
         }
-        const unsigned char* hb = hstream + (size_t)rank * HEAD_BYTES;
-        for (int ch = 0; ch < N_HEAD && run; ++ch) run = push(hb + (size_t)ch * CH_HEAD, CH_HEAD);
         ++steps_done;
       }
       // drain: every copy that was issued but never consumed must land before the CTA may exit
       for (unsigned i = sm.consumed; i < issued; ++i) mbar_wait(&sm.full[ring_slot(i)], ring_par(i));
+    }
+  } else if (warp == NCW + 1) {
+    // ---------------- producer 2: weight stream -> L2 two units ahead; the layer vectors -> their own 2-deep ring ----------
+    if (lane == 0) {
+      unsigned vissued = 0;
+      bool run = true;
+      for (int u = 0; run; ++u) {  // unit u = layer (u % units_per_step), or the head
+        while (sm.unit_seq + 2 < u) { if (sm.stop) { run = false; break; } }
+        if (!run) break;
+        const int layer = u % units_per_step;
+        if (layer < c.n_layer) {
+          const unsigned char* base = wstream + ((size_t)layer * C + rank) * LAYER_BYTES;
+          for (int o = 0; o < LAYER_BYTES; o += 32768) l2_prefetch(base + o, (uint32_t)min(32768, LAYER_BYTES - o));
+          const unsigned vs = vissued & 1u, vp = ((vissued >> 1) & 1u) ^ 1u;
+          while (!mbar_try(&sm.vempty[vs], vp)) { if (sm.stop) { run = false; break; } }
+          if (!run) break;
+          mbar_expect_tx(&sm.vfull[vs], CH_VEC);
+          bulk_load(sm.vec[vs], base + OFFS_VEC, CH_VEC, &sm.vfull[vs]);
+          ++vissued;
+        } else {
+          const unsigned char* hb = hstream + (size_t)rank * HEAD_BYTES;
+          for (int o = 0; o < HEAD_BYTES; o += 32768) l2_prefetch(hb + o, (uint32_t)min(32768, HEAD_BYTES - o));
+        }
+      }
       for (unsigned i = sm.vconsumed; i < vissued; ++i) mbar_wait(&sm.vfull[i & 1u], (i >> 1) & 1u);
     }
   } else {
@@ -557,7 +544,11 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
     SampSmem& ss = *reinterpret_cast<SampSmem*>(sm.e13);
     long long* tl = nullptr;  // measurement hook: clock stamps of thread 0 at the markers of one step
     int tk = 0;
+    int unit = 0;
 #define CS_TL() do { if (tl && tid == 0 && tk < 2 * c.tl_slots) tl[tk++] = clock64(); } while (0)
+    // this warp's fragment streams inside a layer block (uint4 units), + lane
+    const size_t wq = (OFFS_QKV + (size_t)warp * NF_QKV * 512) / 16 + lane, wo = (OFFS_WO + (size_t)warp * NF_WO * 512) / 16 + lane,
+                 w1 = (OFFS_W1 + (size_t)warp * NF_W1 * 512) / 16 + lane, w2 = (OFFS_W2 + (size_t)warp * NF_W2 * 512) / 16 + lane;
     for (int it = 0; it < max_new_steps; ++it) {
       const int n_act = ld_cg_i(c.n_active);
       if (n_act == 0 || __ldcg(c.abort_flag) != 0) break;
@@ -566,6 +557,9 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
       CS_TL();
       const int R = ((int)cid < n_act) ? (n_act - (int)cid + (int)ncl - 1) / (int)ncl : 0;  // rows r = n*ncl + cid
       if (R > 0) {
+        uint4 wf[FB];  // first fragment batch of the next matrix, in flight across the hand-off that precedes it
+        const uint4* lw = reinterpret_cast<const uint4*>(wstream + (size_t)rank * LAYER_BYTES);
+        if (warp < NW_QKV) ldg_batch(lw + wq, wf);
         // ---- step prologue: row descriptors, page-table rows, layer-0 input
         if (tid < R) {
           const int r = tid * ncl + cid;
@@ -574,9 +568,9 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           sm.row_kvoff[tid] = __ldcg(c.row_kvoff + r);
         }
         csync();
-        for (int i = tid; i < R * 64; i += NCW * 32) {
-          const int n = i >> 6, pg = i & 63;
-          sm.pt[n][pg] = (pg <= (sm.row_pos[n] >> 6)) ? c.page_table[sm.row_slot[n] * c.max_pages + pg] : 0;
+        for (int i = tid; i < R * 32; i += NCW * 32) {
+          const int n = i >> 5, pg = i & 31;
+          sm.pt[n][pg] = (pg <= (sm.row_pos[n] >> PAGE_SHIFT)) ? c.page_table[sm.row_slot[n] * c.max_pages + pg] : 0;
         }
         if (warp < R) {
           const int n = warp;
@@ -591,9 +585,10 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           sm.xres[n][lane] = ld_cg_f(xr + rank * HD + lane);
         }
         csync();
-        if (tid == 0) { sm.n_rows = R; __threadfence_block(); sm.step_seq = sm.step_seq + 1; }  // producer may list this step's K/V
+        if (tid == 0) { sm.n_rows = R; __threadfence_block(); sm.step_seq = sm.step_seq + 1; }  // the K/V producer may list this step
         CS_TL();
         for (int layer = 0; layer < c.n_layer; ++layer) {
+          if (tid == 0) sm.unit_seq = ++unit;
           // ---- the layer's vectors (own 2-deep ring; normally long landed)
           const unsigned vslot = vcons & 1u;
           mbar_wait(&sm.vfull[vslot], (vcons >> 1) & 1u);
@@ -602,9 +597,10 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- QKV for head `rank` (warps 0..5: q lo/hi, k lo/hi, v lo/hi)
           {
             float acc[4];
-            gemv_stream<N_QKV, 6>(sm, cons, &sm.xn[0][0], XS8, 0, acc);
+            if (warp < NW_QKV) gemv_ldg<NF_QKV>(lw + wq, wf, &sm.xn[0][0], XS8, 0, acc);
+            ldg_batch(lw + wo, wf);  // Wo's only batch: in flight during the attention
             CS_TL();
-            if (warp < 6) {
+            if (warp < NW_QKV) {
               const int ty = warp >> 1, f0 = (warp & 1) * 16 + g;
               const float b0 = vec[VC_BQ + ty * HD + f0], b1 = vec[VC_BQ + ty * HD + f0 + 8];
               const float v00 = acc[0] + b0, v01 = acc[1] + b0, v10 = acc[2] + b1, v11 = acc[3] + b1;  // (feature, sequence 2t | 2t+1)
@@ -614,7 +610,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
                 sm.q[n0][f0 + 8] = v10 * QSCALE; sm.q[n1][f0 + 8] = v11 * QSCALE;
               } else {
                 bf16 (*dst)[HD] = (ty == 1) ? sm.knew : sm.vnew;
-                bf16* pool = ((ty == 1) ? c.kpool : c.vpool) + (size_t)layer * c.kv_layer_stride + (size_t)rank * (PAGE * DH);
+                bf16* pool = ((ty == 1) ? c.kpool : c.vpool) + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE;
                 const bf16 h00 = __float2bfloat16_rn(v00), h01 = __float2bfloat16_rn(v01), h10 = __float2bfloat16_rn(v10),
                            h11 = __float2bfloat16_rn(v11);
                 dst[n0][f0] = h00; dst[n1][f0] = h01; dst[n0][f0 + 8] = h10; dst[n1][f0 + 8] = h11;
@@ -635,7 +631,8 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- O-projection (32 outputs, split-K over warp pairs) + bias + residual -> exchange 2
           {
             float acc[4];
-            gemv_stream<N_WO, NCW>(sm, cons, reinterpret_cast<const bf16*>(sm.e13), XS8, (warp >> 1) * 8, acc);
+            gemv_ldg<NF_WO>(lw + wo, wf, reinterpret_cast<const bf16*>(sm.e13), XS8, (warp >> 1) * 8, acc);
+            ldg_batch(lw + w1, wf);  // FFN1's first batch: in flight during the epilogue, hand-off 2 and LayerNorm 1
             CS_TL();
             if (tid == 0) mbar_expect_tx(&sm.ebar[1], (uint32_t)R * (D * 2 + C * 8));
             residual_epilogue(sm, acc, R, vec + VC_BO, rank, e24_addr, st_addr, eb[1]);
@@ -649,7 +646,8 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- FFN1 (128 hidden units, one tile per warp) + bias + ReLU -> exchange 3
           {
             float acc[4];
-            gemv_stream<N_W1, NCW>(sm, cons, &sm.xn[0][0], XS8, 0, acc);
+            gemv_ldg<NF_W1>(lw + w1, wf, &sm.xn[0][0], XS8, 0, acc);
+            ldg_batch(lw + w2, wf);  // FFN2's first batch: in flight during hand-off 3
             CS_TL();
             const int f0 = warp * 16 + g;
             const float b0 = vec[VC_B1 + f0], b1 = vec[VC_B1 + f0 + 8];
@@ -667,7 +665,14 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- FFN2 (32 outputs, K = 2048 split over warp pairs) + bias + residual -> exchange 4
           {
             float acc[4];
-            gemv_stream<N_W2, NCW>(sm, cons, reinterpret_cast<const bf16*>(sm.e13), HS8, (warp >> 1) * 32, acc);
+            gemv_ldg<NF_W2>(lw + w2, wf, reinterpret_cast<const bf16*>(sm.e13), HS8, (warp >> 1) * 32, acc);
+            // next unit's first batch (QKV of the next layer, or the head) in flight during hand-off 4 and LayerNorm 2
+            if (layer + 1 < c.n_layer) {
+              lw += (size_t)C * LAYER_BYTES / 16;
+              if (warp < NW_QKV) ldg_batch(lw + wq, wf);
+            } else if (warp < HEAD_TILES) {
+              ldg_batch(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf);
+            }
             CS_TL();
             if (tid == 0) mbar_expect_tx(&sm.ebar[3], (uint32_t)R * (D * 2 + C * 8));
             residual_epilogue(sm, acc, R, vec + VC_B2, rank, e24_addr, st_addr, eb[3]);
@@ -681,11 +686,12 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           CS_TL();
         }
         // ---- head: vocabulary tiles rank, rank+16, ... (warps 0..4) -> logits in global memory
+        if (tid == 0) sm.unit_seq = ++unit;
         {
           float acc[4];
-          gemv_stream<N_HEAD, HEAD_TILES>(sm, cons, &sm.xn[0][0], XS8, 0, acc);
-          CS_TL();
           if (warp < HEAD_TILES) {
+            gemv_ldg<NF_HEAD>(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf,
+                              &sm.xn[0][0], XS8, 0, acc);
             const int f0 = ((int)rank + C * warp) * 16 + g;
             const int n0 = 2 * t, n1 = 2 * t + 1;
             if (n0 < R) {
@@ -699,6 +705,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
               if (f0 + 8 < V) lg[f0 + 8] = acc[3];
             }
           }
+          CS_TL();
         }
         // ---- cluster barrier that also orders the global logits writes (release / acquire at cluster scope)
         csync();

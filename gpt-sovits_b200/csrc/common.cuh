@@ -16,7 +16,8 @@ constexpr int V = 1025;         // vocab incl. EOS
 constexpr int VT = 65;          // 16-row feature tiles of the head (1040 rows, zero padded)
 constexpr int VPAD = VT * 16;
 constexpr int BERT = 1024;
-constexpr int PAGE = 64;        // KV positions per page
+constexpr int PAGE = 128;       // KV positions per page
+constexpr int PAGE_SHIFT = 7;
 constexpr int MAX_B = 256;      // max utterances per call
 constexpr int NT = 256;         // threads per CTA in every phase kernel
 constexpr int NW = NT / 32;
@@ -38,11 +39,15 @@ constexpr int VO_BQKV = 0, VO_BO = 1536, VO_B1 = 2048, VO_B2 = 4096, VO_G1 = 460
               // LayerNorm folded into the consumer GEMMs (k_fold_ln): c1 = Wg 1, c0 = W beta + bias
               VO_C1_QKV = 6656, VO_C0_QKV = 8192, VO_C1_FFN1 = 9728, VO_C0_FFN1 = 11776, LV = 13824;
 
-// KV cache layout inside one layer's pool: [page][head][position in page][head dim] bf16, i.e. the K (or V) of one head
-// for one 64-position page is a contiguous 4 KB block (a TMA bulk copy can fetch it).  A row's `kvoff` is the element
-// offset of (its page, head 0, its position, dim 0); feature f = head*32 + dim lives kv_feat(f) elements further.
-__host__ __device__ constexpr long long kv_row_off(long long page, int pos_in_page) { return page * PAGE * D + (long long)pos_in_page * DH; }
-__host__ __device__ constexpr int kv_feat(int f) { return (f >> 5) * (PAGE * DH) + (f & (DH - 1)); }
+// KV cache layout inside one layer's pool: [page][head][K: 128 positions x 32 dims | V: 128 x 32] bf16, i.e. everything one
+// head needs of one 128-position page is ONE contiguous 16 KB block (K 8 KB, then V 8 KB): a single TMA bulk copy fetches
+// it.  K and V share the pool: vpool = kpool + KV_V_OFF.  A row's `kvoff` is the element offset of (its page, head 0, its
+// position, dim 0); feature f = head*32 + dim lives kv_feat(f) elements further.
+constexpr int KV_HEAD_STRIDE = 2 * PAGE * DH;       // elements between heads inside a page (K block + V block)
+constexpr int KV_PAGE_STRIDE = NH * KV_HEAD_STRIDE; // elements per page (all heads, K and V)
+constexpr int KV_V_OFF = PAGE * DH;                 // V block behind the K block
+__host__ __device__ constexpr long long kv_row_off(long long page, int pos_in_page) { return page * KV_PAGE_STRIDE + (long long)pos_in_page * DH; }
+__host__ __device__ constexpr int kv_feat(int f) { return (f >> 5) * KV_HEAD_STRIDE + (f & (DH - 1)); }
 
 constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
 
@@ -64,7 +69,7 @@ struct Ctx {
   float alpha_audio, alpha_text;
   int n_layer;
   int pe_len;
-  // KV cache: pools [n_layer][n_pages][NH][PAGE][DH] bf16 (see kv_row_off), page table [B][max_pages]
+  // KV cache: one pool [n_layer][n_pages][NH][K|V][PAGE][DH] bf16 (see kv_row_off; vpool = kpool + KV_V_OFF), page table [B][max_pages]
   bf16* kpool;
   bf16* vpool;
   size_t kv_layer_stride;

@@ -491,9 +491,9 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
     for (int i = 0; i < np; ++i) page_table[(size_t)b * max_pages + i] = (int)pages++;
   }
   if (pages > e->pool_pages) {
-    const size_t bytes = (size_t)e->cfg.n_layer * pages * PAGE * D * 2;
+    const size_t bytes = (size_t)e->cfg.n_layer * pages * KV_PAGE_STRIDE * 2;  // K and V interleaved per (page, head)
     CK(cudaStreamSynchronize(s));
-    if (e->kpool.ensure(bytes) || e->vpool.ensure(bytes)) return 1;
+    if (e->kpool.ensure(bytes)) return 1;
     e->pool_pages = pages;
   }
   // ---- host-built index arrays
@@ -549,7 +549,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
   std::vector<long long> kvoff(T);
   for (int r = 0; r < T; ++r)
-    kvoff[r] = kv_row_off(page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> 6)], row_pos[r] & (PAGE - 1));
+    kvoff[r] = kv_row_off(page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> PAGE_SHIFT)], row_pos[r] & (PAGE - 1));
   CK(cudaMemcpyAsync(e->kvoff.p, kvoff.data(), (size_t)T * 8, cudaMemcpyHostToDevice, s));
   int* di = e->ints.as<int>();
   e->d_row_slot = di + o_row_slot; e->d_row_pos = di + o_row_pos; e->d_head_rows = di + o_head;
@@ -606,8 +606,8 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
   c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
   c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
-  c.kpool = e->kpool.as<bf16>(); c.vpool = e->vpool.as<bf16>();
-  c.kv_layer_stride = e->pool_pages * PAGE * D;
+  c.kpool = e->kpool.as<bf16>(); c.vpool = c.kpool + KV_V_OFF;
+  c.kv_layer_stride = e->pool_pages * (size_t)KV_PAGE_STRIDE;
   c.page_table = e->d_page_table; c.max_pages = max_pages;
   int* i2 = e->ints2.as<int>();
   c.n_rows = i2 + 0; c.n_active = i2 + 1; c.step = i2 + 2; c.abort_flag = i2 + 3;
@@ -739,7 +739,7 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
     if (mode == 4) {
       if (e->max_clusters < 1) return fail("t2s_decode: cluster-stream decode unavailable (no co-resident 16-CTA cluster)");
       if (e->B > e->max_clusters * cs::RMAX) return fail("t2s_decode: cluster-stream decode holds at most %d sequences (got %d)", e->max_clusters * cs::RMAX, e->B);
-      if (e->cd.max_pages > 64) return fail("t2s_decode: cluster-stream decode supports at most 64 KV pages per sequence");
+      if (e->cd.max_pages > 32) return fail("t2s_decode: cluster-stream decode supports at most 32 KV pages per sequence");
     }
     e->st.decode_mode = mode;
     if (mode == 4) {

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(64) k_prefill_attn(Ctx c, int layer, const QTi
     {
       const int p = kt + tid;
       if (p < kv_end) {
-        const size_t off = (size_t)kv_row_off(pt[p >> 6], p & (PAGE - 1)) + (size_t)head * (PAGE * DH);
+        const size_t off = (size_t)kv_row_off(pt[p >> PAGE_SHIFT], p & (PAGE - 1)) + (size_t)head * KV_HEAD_STRIDE;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const uint4 kk = *reinterpret_cast<const uint4*>(kbase + off + ch * 8);

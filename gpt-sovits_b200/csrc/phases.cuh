@@ -395,18 +395,18 @@ __device__ __forceinline__ void attn_merge_write(const Ctx& c, AttnSmem& sm, int
 template <int U>
 __device__ __forceinline__ void attn_load(const bf16* kbase, const bf16* vbase, const int* pt, int p0, int pend, int lane,
                                           uint4 (&ka)[U], uint4 (&kb)[U], uint4 (&va)[U], uint4 (&vb)[U]) {
-  const int page = pt[p0 >> 6];
+  const int page = pt[p0 >> PAGE_SHIFT];
   // lane l: 16-byte chunk of head l/4 (dims 8*(l%4)..+7) and of head 8 + l/4 (head-major pages, see kv_row_off)
-  const size_t rowoff = (size_t)kv_row_off(page, p0 & (PAGE - 1)) + (size_t)(lane >> 2) * (PAGE * DH) + (lane & 3) * 8;
+  const size_t rowoff = (size_t)kv_row_off(page, p0 & (PAGE - 1)) + (size_t)(lane >> 2) * KV_HEAD_STRIDE + (lane & 3) * 8;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (p0 + u < pend) {
       const bf16* kr = kbase + rowoff + (size_t)u * DH;
       const bf16* vr = vbase + rowoff + (size_t)u * DH;
       ka[u] = ld_cg16(kr);
-      kb[u] = ld_cg16(kr + 8 * PAGE * DH);
+      kb[u] = ld_cg16(kr + 8 * KV_HEAD_STRIDE);
       va[u] = ld_cg16(vr);
-      vb[u] = ld_cg16(vr + 8 * PAGE * DH);
+      vb[u] = ld_cg16(vr + 8 * KV_HEAD_STRIDE);
     } else {
       ka[u] = kb[u] = va[u] = vb[u] = make_uint4(0, 0, 0, 0);
     }
@@ -900,7 +900,7 @@ __device__ void phase_plan(const Ctx& c, int* smem_i) {
     c.active[p] = slot;
     c.row_slot[p] = slot;
     c.row_pos[p] = pos;
-    c.row_kvoff[p] = kv_row_off(c.page_table[slot * c.max_pages + (pos >> 6)], pos & (PAGE - 1));
+    c.row_kvoff[p] = kv_row_off(c.page_table[slot * c.max_pages + (pos >> PAGE_SHIFT)], pos & (PAGE - 1));
     c.seq_len[slot] = pos + 1;
     kvpos = (unsigned long long)(pos + 1);
   }
