@@ -49,16 +49,24 @@ constexpr int OFFS_VEC = 0, OFFS_QKV = CH_VEC, OFFS_WO = OFFS_QKV + SZ_QKV, OFFS
               LAYER_BYTES = OFFS_W2 + SZ_W2;  // 402,560
 constexpr int HEAD_TILES = 5;    // 16-row tiles of ar_predict_layer per CTA (80 >= 65)
 constexpr int NF_HEAD = 32, HEAD_BYTES = HEAD_TILES * NF_HEAD * 512;  // 81,920
-constexpr int XS8 = D + 8;       // bf16 row stride of a 512-wide operand (bank-conflict-free B fragments)
-constexpr int HS8 = FF + 8;
+constexpr int XS8 = D + 8;       // bf16 row stride of the local 512-wide operand xn (bank-conflict-free B fragments)
+// Hand-off buffers are laid out per SOURCE CTA so that a source's whole contribution is one contiguous block = one bulk
+// copy: block = [optional 64 B of per-row statistics][RMAX rows x (slice + 16 B pad)].  The pad makes the rows of a block
+// fall into distinct banks for the MMA B-fragment loads (row stride 80 B / 272 B).
+constexpr int ROW_S = HD * 2 + 16;             // 80 B: a 32-feature bf16 slice row
+constexpr int ROW_H = FH * 2 + 16;             // 272 B: a 128-feature bf16 slice row (FFN hidden)
+constexpr int BLK_A = RMAX * ROW_S;            // 640 B: attention-out block of one source
+constexpr int BLK_H = RMAX * ROW_H;            // 2176 B: FFN-hidden block of one source
+constexpr int BLK_ST = RMAX * 8;               // 64 B: (sum, sum of squares) per row, in front of a residual block
+constexpr int BLK_Y = BLK_ST + RMAX * ROW_S;   // 704 B: residual-sum block of one source
 static_assert(LAYER_BYTES == (3 * D * D + D * D + 2 * FF * D) * 2 / C + CH_VEC && CH_VEC % 16 == 0, "stream size");
+static_assert(NSLOT == NCW, "ring slot i is read by warp i");
 static_assert(SLOT == KV_HEAD_STRIDE * 2, "one ring slot = one (page, head) K|V block");
 
 struct __align__(128) Smem {
   unsigned char ring[NSLOT][SLOT];
-  unsigned char e13[RMAX * HS8 * 2];  // E1: attention out bf16 [RMAX][XS8]; E3: FFN hidden bf16 [RMAX][HS8]; sampler scratch
-  bf16 e24[RMAX][XS8];                // E2 / E4: residual sums (pre-LayerNorm) of all 512 features, bf16
-  float2 st24[RMAX][C];               // (sum, sum of squares) of every peer's 32-feature slice (fp32, from unrounded values)
+  alignas(16) unsigned char e13[C * BLK_H];  // E1: attention out, C blocks of BLK_A; E3: FFN hidden, C blocks of BLK_H; sampler scratch
+  alignas(16) unsigned char e24[C * BLK_Y];  // E2 / E4: residual sums (pre-LayerNorm), C blocks of BLK_Y (statistics + bf16 rows)
   bf16 xn[RMAX][XS8];                 // LayerNorm'ed rows: operand of QKV / FFN1 / head
   float yown[RMAX][HD];               // own slice of the current residual sum, fp32
   float xres[RMAX][HD];               // own slice of the LayerNorm output (the next residual), fp32
@@ -66,7 +74,7 @@ struct __align__(128) Smem {
   bf16 knew[RMAX][HD];
   bf16 vnew[RMAX][HD];
   float red[NCW][16][RMAX + 1];
-  unsigned char stage[RMAX * FH * 2]; // outgoing slice, bf16 [R][32] or [R][128]
+  alignas(16) unsigned char stage[2][BLK_H];  // outgoing block (same layout as the destination block), double buffered
   float am[NCW][RMAX], al[NCW][RMAX], aacc[NCW][RMAX][HD];
   int pt[RMAX][32];                   // page-table rows of this cluster's sequences (<= 32 pages of 128 positions)
   int row_slot[RMAX], row_pos[RMAX];
@@ -116,14 +124,12 @@ __device__ __forceinline__ uint32_t n_clusters() { uint32_t r; asm volatile("mov
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
-__device__ __forceinline__ void st_async16(uint32_t addr, const uint4& v, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(addr),
-               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
+// shared::cta -> (remote) shared::cluster bulk copy; completes `bytes` on the destination CTA's mbarrier
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
-__device__ __forceinline__ void st_async8(uint32_t addr, float a, float b, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];" ::"r"(addr),
-               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(mbar) : "memory");
-}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -221,17 +227,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Weight fragments come straight from L2 (prefetched there two layers ahead): 8 x 128-bit loads in flight per lane.
-constexpr int FB = 8;  // fragments per batch
+// Weight fragments come straight from L2 (prefetched there two layers ahead) into a rolling buffer of FB 128-bit
+// registers per lane: fragment k+FB is requested the moment fragment k has been fed to the tensor core, so FB loads stay
+// in flight per lane (8 KB per warp, 64 KB per SM) for the whole matrix.
+constexpr int FB = 16;
+template <int N>
 __device__ __forceinline__ void ldg_batch(const uint4* p, uint4 (&f)[FB]) {  // p = warp's fragment base + lane
 #pragma unroll
-  for (int i = 0; i < FB; ++i) f[i] = ld_weight16(p + i * 32);
+  for (int i = 0; i < N; ++i) f[i] = ld_weight16(p + i * 32);
 }
-// One matrix slice of this warp = NF fragments (k-blocks kb0 .. kb0+NF-1 of one 16-feature tile), `first` = its first batch
-// (already in flight / landed).  acc = 16 features x 8 sequences in the m16n8k16 C layout (c0,c1: feature g, sequences
-// 2t,2t+1; c2,c3: feature g+8).  act: bf16 activation rows (row stride astride elements).
-template <int NF>
-__device__ __forceinline__ void gemv_ldg(const uint4* wp, uint4 (&first)[FB], const bf16* act, int astride, int kb0, float (&acc)[4]) {
+// One matrix slice of this warp = NF fragments (k-blocks kb0 .. kb0+NF-1 of one 16-feature tile); buf = its first
+// min(NF, FB) fragments (already in flight / landed).  acc = 16 features x 8 sequences in the m16n8k16 C layout (c0,c1:
+// feature g, sequences 2t,2t+1; c2,c3: feature g+8).  act: bf16 activation rows (row stride astride elements).
+// The activation element (sequence g, k-block kb) lives at act + g*ROWS + (kb / SKB)*SRCS + (kb % SKB)*16 (elements): SKB
+// k-blocks per source block, SRCS elements between source blocks (local operand xn: one "source", ROWS = XS8).
+template <int NF, int SKB, int SRCS, int ROWS>
+__device__ __forceinline__ void gemv_ldg(const uint4* wp, uint4 (&buf)[FB], const bf16* act, int kb0, float (&acc)[4]) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float a[4][4];
@@ -239,34 +250,26 @@ __device__ __forceinline__ void gemv_ldg(const uint4* wp, uint4 (&first)[FB], co
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
-  const bf16* arow = act + (size_t)g * astride + kb0 * 16;
-  uint4 nxt[FB];
+  const bf16* arow = act + g * ROWS + (kb0 / SKB) * SRCS;  // kb0 is a multiple of SKB
 #pragma unroll
-  for (int b = 0; b < NF / FB; ++b) {
-    if (b + 1 < NF / FB) ldg_batch(wp + (b + 1) * FB * 32, nxt);
-#pragma unroll
-    for (int i = 0; i < FB; ++i) {
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(arow + (b * FB + i) * 16);
-      mma_bf16_16816(a[i & 3], first[i], xr[t], xr[4 + t]);
-    }
-    if (b + 1 < NF / FB) {
-#pragma unroll
-      for (int i = 0; i < FB; ++i) first[i] = nxt[i];
-    }
+  for (int k = 0; k < NF; ++k) {
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(arow + (k / SKB) * SRCS + (k % SKB) * 16);
+    mma_bf16_16816(a[k & 3], buf[k % FB], xr[t], xr[4 + t]);
+    if (k + FB < NF) buf[k % FB] = ld_weight16(wp + (k + FB) * 32);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = (a[0][j] + a[1][j]) + (a[2][j] + a[3][j]);
 }
 
-// All-gather through DSMEM: every CTA sends `PIECES` 16-byte pieces per row (its slice, staged in sm.stage with row
-// stride PIECES*16 B) to every peer's buffer `dst` (row stride dst_stride bytes) at byte column rank*PIECES*16.
-template <int PIECES>
-__device__ __forceinline__ void all_gather(Smem& sm, uint32_t dst, int dst_stride, int R, uint32_t rank, uint32_t ebar) {
-  const int total = R * PIECES * C;
-  for (int i = threadIdx.x; i < total; i += NCW * 32) {
-    const int peer = i & (C - 1), pc = (i >> 4) % PIECES, n = (i >> 4) / PIECES;
-    const uint4 v = *reinterpret_cast<const uint4*>(sm.stage + (n * PIECES + pc) * 16);
-    st_async16(mapa(dst + n * dst_stride + (rank * PIECES + pc) * 16, peer), v, mapa(ebar, peer));
+// All-gather through DSMEM: this CTA's block (staged in `src`, written by generic stores that the callers fenced for the
+// async proxy and ordered by a CTA barrier) goes to slot `rank` of every peer's buffer `dst` with one bulk copy per peer;
+// the copy completes its bytes on the peer's mbarrier, so data and "ready" travel together.  Two lanes of every warp
+// issue (one copy each).
+__device__ __forceinline__ void all_gather(uint32_t src, uint32_t dst, uint32_t blk, uint32_t bytes, uint32_t rank, uint32_t ebar) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < C / NCW) {
+    const uint32_t peer = warp * (C / NCW) + lane;
+    bulk_s2s(mapa(dst + rank * blk, peer), src, bytes, mapa(ebar, peer));
   }
 }
 
@@ -275,7 +278,7 @@ __device__ __forceinline__ void layer_norm_rows(Smem& sm, int R, uint32_t rank, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < R) {
     const int n = warp;
-    const float2 p = (lane < C) ? sm.st24[n][lane] : make_float2(0.f, 0.f);
+    const float2 p = (lane < C) ? *reinterpret_cast<const float2*>(sm.e24 + lane * BLK_Y + n * 8) : make_float2(0.f, 0.f);
     const float s = warp_sum(p.x), qq = warp_sum(p.y);
     const float mean = s * (1.0f / D);
     const float var = fmaxf(qq * (1.0f / D) - mean * mean, 0.f);
@@ -283,7 +286,8 @@ __device__ __forceinline__ void layer_norm_rows(Smem& sm, int R, uint32_t rank, 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k0 = h * 256 + lane * 8;
-      const uint4 raw = *reinterpret_cast<const uint4*>(&sm.e24[n][k0]);
+      // features k0..k0+7 = source block k0/32, 16-byte piece (lane & 3) of its row n
+      const uint4 raw = *reinterpret_cast<const uint4*>(sm.e24 + (k0 >> 5) * BLK_Y + BLK_ST + n * ROW_S + (lane & 3) * 16);
       const float4 g0 = *reinterpret_cast<const float4*>(gam + k0), g1 = *reinterpret_cast<const float4*>(gam + k0 + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(bet + k0), b1 = *reinterpret_cast<const float4*>(bet + k0 + 4);
       uint4 o;
@@ -301,7 +305,7 @@ __device__ __forceinline__ void layer_norm_rows(Smem& sm, int R, uint32_t rank, 
 // Split-K epilogue of Wo / W2: warp w holds the partial of tile (w&1), K quarter (w>>1).  Reduce the four quarters in a
 // fixed order, add bias + residual -> yown (fp32) and the outgoing bf16 slice + partial LayerNorm statistics.
 __device__ __forceinline__ void residual_epilogue(Smem& sm, const float (&acc)[4], int R, const float* bias, uint32_t rank,
-                                                  uint32_t e24_addr, uint32_t st_addr, uint32_t ebar) {
+                                                  unsigned char* stage, uint32_t e24_addr, uint32_t ebar) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int g = lane >> 2, t = lane & 3;
   sm.red[warp][g][2 * t] = acc[0]; sm.red[warp][g][2 * t + 1] = acc[1];
@@ -315,20 +319,21 @@ __device__ __forceinline__ void residual_epilogue(Smem& sm, const float (&acc)[4
       const float s = (sm.red[tl][fr][n] + sm.red[tl + 2][fr][n]) + (sm.red[tl + 4][fr][n] + sm.red[tl + 6][fr][n]);
       y = s + bias[fl] + sm.xres[n][fl];
       sm.yown[n][fl] = y;
-      reinterpret_cast<bf16*>(sm.stage)[n * HD + fl] = __float2bfloat16_rn(y);
+      *reinterpret_cast<bf16*>(stage + BLK_ST + n * ROW_S + fl * 2) = __float2bfloat16_rn(y);
     }
     const float s1 = warp_sum(y), s2 = warp_sum(y * y);
-    if (n < R && fl < C) st_async8(mapa(st_addr + (n * C + rank) * 8, fl), s1, s2, mapa(ebar, fl));
+    if (n < R && fl == 0) *reinterpret_cast<float2*>(stage + n * 8) = make_float2(s1, s2);
   }
+  fence_proxy_async_smem();
   csync();
-  all_gather<HD * 2 / 16>(sm, e24_addr, XS8 * 2, R, rank, ebar);
+  all_gather(s32(stage), e24_addr, BLK_Y, BLK_ST + R * ROW_S, rank, ebar);
 }
 
 // Single-query attention of head `rank` for the cluster's R sequences.  The cached positions [0, pos) arrive through the
 // ring, one 128-position page per slot: K rows at byte i*64, V rows at 8192 + i*64.  Position `pos` (this step's token)
-// comes from shared memory.  Warp w takes positions 16w..16w+15 of a page; a quad of lanes owns two of them (4 x 16 B =
-// the head's 32 dims each), scores both, then folds them into its online-softmax state in one update; quads, then warps
-// are merged in a fixed order.
+// comes from shared memory.  A page is processed by ONE warp (ring chunk i -> warp i % 8 = ring slot i % 8): a quad of lanes
+// owns positions quad, quad+8, ... (4 x 16 B = the head's 32 dims each), scores four of them, then folds them into its
+// online-softmax state in one update; the quads of a warp, then the warps are merged in a fixed order.
 __device__ __forceinline__ float dot8(const float (&q)[8], const uint4& k) {
   return q[0] * bf_lo(k.x) + q[1] * bf_hi(k.x) + q[2] * bf_lo(k.y) + q[3] * bf_hi(k.y) + q[4] * bf_lo(k.z) + q[5] * bf_hi(k.z) +
          q[6] * bf_lo(k.w) + q[7] * bf_hi(k.w);
@@ -337,94 +342,114 @@ __device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) 
   acc[0] += p * bf_lo(v.x); acc[1] += p * bf_hi(v.x); acc[2] += p * bf_lo(v.y); acc[3] += p * bf_hi(v.y);
   acc[4] += p * bf_lo(v.z); acc[5] += p * bf_hi(v.z); acc[6] += p * bf_lo(v.w); acc[7] += p * bf_hi(v.w);
 }
-__device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R) {
+__device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R, unsigned char* stage) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quad = lane >> 2, part = lane & 3;
+  unsigned j = cons;  // ring index of the next page (same order as the producer: sequences, then pages)
   for (int n = 0; n < R; ++n) {
     const int pos = sm.row_pos[n];
-    float qv[8];
+    const int npg = (pos + PAGE - 1) >> PAGE_SHIFT;
+    // ring chunk i (a whole page) belongs to warp i % 8 = the warp that always reads ring slot i % 8: every warp sees the
+    // phases of its slot strictly in order (an mbarrier parity wait must never run a phase ahead), pages are spread evenly
+    const int first = (warp - (int)j) & (NCW - 1);
+    if (first < npg) {
+      float qv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) qv[j] = sm.q[n][part * 8 + j];
-    float m = -INFINITY, l = 0.f, acc[8];
+      for (int i = 0; i < 8; ++i) qv[i] = sm.q[n][part * 8 + i];
+      float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    {  // this step's token: warp 0, quad 0
-      const uint4 kk = *reinterpret_cast<const uint4*>(&sm.knew[n][part * 8]);
-      float s = dot8(qv, kk);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (warp == 0 && quad == 0) {
-        m = s; l = 1.f;
-        axpy8(acc, 1.f, *reinterpret_cast<const uint4*>(&sm.vnew[n][part * 8]));
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int pg = first; pg < npg; pg += NCW) {
+        const int np = min(PAGE, pos - pg * PAGE);
+        const unsigned slot = ring_slot(j + pg);
+        mbar_wait(&sm.full[slot], ring_par(j + pg));
+        const unsigned char* kb = sm.ring[slot] + part * 16;
+        for (int u0 = 0; u0 * 8 < np; u0 += 4) {  // 4 positions per quad per round: 32 positions per warp round
+          uint4 kk[4], vv[4];
+          bool ok[4];
+          float sc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = (u0 + u) * 8 + quad;
+            ok[u] = i < np;
+            const int ic = ok[u] ? i : 0;
+            kk[u] = *reinterpret_cast<const uint4*>(kb + ic * 64);
+            vv[u] = *reinterpret_cast<const uint4*>(kb + 8192 + ic * 64);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sc[u] = dot8(qv, kk[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
+          float mn = m;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (ok[u]) mn = fmaxf(mn, sc[u]);
+          if (ok[0]) {  // ok[u] implies ok[0]
+            const float corr = fast_exp2(m - mn);
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = ok[u] ? fast_exp2(sc[u] - mn) : 0.f;
+            m = mn;
+            l = l * corr + (e[0] + e[1]) + (e[2] + e[3]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) axpy8(acc, e[u], vv[u]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[slot]);
       }
-    }
-    for (int p0 = 0; p0 < pos; p0 += PAGE) {
-      const int np = min(PAGE, pos - p0);
-      const unsigned slot = ring_slot(cons);
-      mbar_wait(&sm.full[slot], ring_par(cons));
-      const unsigned char* kb = sm.ring[slot] + part * 16;
-      const int i0 = warp * 16 + quad, i1 = i0 + 8;
-      const bool ok0 = i0 < np, ok1 = i1 < np;
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      const uint4 k0 = ok0 ? *reinterpret_cast<const uint4*>(kb + i0 * 64) : z;
-      const uint4 k1 = ok1 ? *reinterpret_cast<const uint4*>(kb + i1 * 64) : z;
-      const uint4 v0 = ok0 ? *reinterpret_cast<const uint4*>(kb + 8192 + i0 * 64) : z;
-      const uint4 v1 = ok1 ? *reinterpret_cast<const uint4*>(kb + 8192 + i1 * 64) : z;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[slot]);
-      ++cons;
-      float s0 = dot8(qv, k0), s1 = dot8(qv, k1);
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      if (ok0) {  // ok1 implies ok0
-        const float mn = fmaxf(m, ok1 ? fmaxf(s0, s1) : s0);
-        const float corr = fast_exp2(m - mn), e0 = fast_exp2(s0 - mn), e1 = ok1 ? fast_exp2(s1 - mn) : 0.f;
+      // merge the 8 quads of the warp (fixed xor tree: deterministic)
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+        const float mn = fmaxf(m, mo);
+        const float ca = (m == -INFINITY) ? 0.f : fast_exp2(m - mn), cb = (mo == -INFINITY) ? 0.f : fast_exp2(mo - mn);
+        l = l * ca + lo * cb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ao = __shfl_xor_sync(0xffffffffu, acc[i], o);
+          acc[i] = acc[i] * ca + ao * cb;
+        }
         m = mn;
-        l = l * corr + e0 + e1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] *= corr;
-        axpy8(acc, e0, v0);
-        axpy8(acc, e1, v1);
       }
-    }
-    // merge the 8 quads of the warp (fixed xor tree: deterministic)
+      if (quad == 0) {
+        if (part == 0) { sm.am[warp][n] = m; sm.al[warp][n] = l; }
 #pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
-      const float mn = fmaxf(m, mo);
-      const float ca = (m == -INFINITY) ? 0.f : fast_exp2(m - mn), cb = (mo == -INFINITY) ? 0.f : fast_exp2(mo - mn);
-      l = l * ca + lo * cb;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float ao = __shfl_xor_sync(0xffffffffu, acc[j], o);
-        acc[j] = acc[j] * ca + ao * cb;
+        for (int i = 0; i < 8; ++i) sm.aacc[warp][n][part * 8 + i] = acc[i];
       }
-      m = mn;
+    } else if (lane == 0) {
+      sm.am[warp][n] = -INFINITY;  // no page of this sequence for this warp
     }
-    if (quad == 0) {
-      if (part == 0) { sm.am[warp][n] = m; sm.al[warp][n] = l; }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sm.aacc[warp][n][part * 8 + j] = acc[j];
-    }
+    j += npg;
   }
+  cons = j;
   csync();
   {
     const int n = threadIdx.x >> 5, d = threadIdx.x & 31;  // warp n = sequence n, lane = head dim
     if (n < R) {
-      float M = -INFINITY;
+      // this step's token (k, v still in shared memory), then the warps' partial states in a fixed order
+      const float s_new = warp_sum(sm.q[n][d] * __bfloat162float(sm.knew[n][d]));
+      float M = s_new;
 #pragma unroll
       for (int w = 0; w < NCW; ++w) M = fmaxf(M, sm.am[w][n]);
-      float L = 0.f, A = 0.f;
+      const float e_new = fast_exp2(s_new - M);
+      float L = e_new, A = e_new * __bfloat162float(sm.vnew[n][d]);
 #pragma unroll
       for (int w = 0; w < NCW; ++w) {
         const float mw = sm.am[w][n];
-        const float sc = (mw == -INFINITY) ? 0.f : fast_exp2(mw - M);
-        L += sm.al[w][n] * sc;
-        A += sm.aacc[w][n][d] * sc;
+        if (mw != -INFINITY) {
+          const float scl = fast_exp2(mw - M);
+          L += sm.al[w][n] * scl;
+          A += sm.aacc[w][n][d] * scl;
+        }
       }
-      reinterpret_cast<bf16*>(sm.stage)[n * HD + d] = __float2bfloat16_rn(A / L);
+      *reinterpret_cast<bf16*>(stage + n * ROW_S + d * 2) = __float2bfloat16_rn(A / L);
     }
   }
+  fence_proxy_async_smem();
   csync();
 }
 
@@ -465,7 +490,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), cid = cluster_idx(), ncl = n_clusters();
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }  // a page is consumed by ONE warp
     for (int k = 0; k < 4; ++k) mbar_init(&sm.ebar[k], 1);
     for (int k = 0; k < 2; ++k) { mbar_init(&sm.vfull[k], 1); mbar_init(&sm.vempty[k], NCW); }
     mbar_init(&sm.cbar, C);
@@ -538,7 +563,8 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
     unsigned cons = 0, vcons = 0;
     uint32_t epar = 0;  // bit k = parity of exchange barrier k
     uint32_t cpar = 0;
-    const uint32_t e13_addr = s32(sm.e13), e24_addr = s32(sm.e24), st_addr = s32(sm.st24);
+    const uint32_t e13_addr = s32(sm.e13), e24_addr = s32(sm.e24);
+    unsigned xch = 0;  // hand-offs so far: staging buffer xch & 1
     const uint32_t eb[4] = {s32(&sm.ebar[0]), s32(&sm.ebar[1]), s32(&sm.ebar[2]), s32(&sm.ebar[3])};
     const int g = lane >> 2, t = lane & 3;
     SampSmem& ss = *reinterpret_cast<SampSmem*>(sm.e13);
@@ -559,7 +585,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
       if (R > 0) {
         uint4 wf[FB];  // first fragment batch of the next matrix, in flight across the hand-off that precedes it
         const uint4* lw = reinterpret_cast<const uint4*>(wstream + (size_t)rank * LAYER_BYTES);
-        if (warp < NW_QKV) ldg_batch(lw + wq, wf);
+        if (warp < NW_QKV) ldg_batch<FB>(lw + wq, wf);
         // ---- step prologue: row descriptors, page-table rows, layer-0 input
         if (tid < R) {
           const int r = tid * ncl + cid;
@@ -597,8 +623,8 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- QKV for head `rank` (warps 0..5: q lo/hi, k lo/hi, v lo/hi)
           {
             float acc[4];
-            if (warp < NW_QKV) gemv_ldg<NF_QKV>(lw + wq, wf, &sm.xn[0][0], XS8, 0, acc);
-            ldg_batch(lw + wo, wf);  // Wo's only batch: in flight during the attention
+            if (warp < NW_QKV) gemv_ldg<NF_QKV, NF_QKV, 0, XS8>(lw + wq, wf, &sm.xn[0][0], 0, acc);
+            ldg_batch<NF_WO>(lw + wo, wf);  // Wo's only batch: in flight during the attention
             CS_TL();
             if (warp < NW_QKV) {
               const int ty = warp >> 1, f0 = (warp & 1) * 16 + g;
@@ -622,20 +648,22 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           }
           // ---- attention, then hand the head's output to every peer (exchange 1)
           CS_TL();
-          attention_rows(sm, cons, R);
+          attention_rows(sm, cons, R, sm.stage[xch & 1]);
           CS_TL();
-          if (tid == 0) mbar_expect_tx(&sm.ebar[0], (uint32_t)R * D * 2);
-          all_gather<HD * 2 / 16>(sm, e13_addr, XS8 * 2, R, rank, eb[0]);
+          if (tid == 0) mbar_expect_tx(&sm.ebar[0], (uint32_t)(C * R * ROW_S));
+          all_gather(s32(sm.stage[xch & 1]), e13_addr, BLK_A, R * ROW_S, rank, eb[0]);
+          ++xch;
           mbar_wait_cluster(&sm.ebar[0], (epar >> 0) & 1u); epar ^= 1u;
           CS_TL();
           // ---- O-projection (32 outputs, split-K over warp pairs) + bias + residual -> exchange 2
           {
             float acc[4];
-            gemv_ldg<NF_WO>(lw + wo, wf, reinterpret_cast<const bf16*>(sm.e13), XS8, (warp >> 1) * 8, acc);
-            ldg_batch(lw + w1, wf);  // FFN1's first batch: in flight during the epilogue, hand-off 2 and LayerNorm 1
+            gemv_ldg<NF_WO, 2, BLK_A / 2, ROW_S / 2>(lw + wo, wf, reinterpret_cast<const bf16*>(sm.e13), (warp >> 1) * 8, acc);
+            ldg_batch<FB>(lw + w1, wf);  // FFN1's first batch: in flight during the epilogue, hand-off 2 and LayerNorm 1
             CS_TL();
-            if (tid == 0) mbar_expect_tx(&sm.ebar[1], (uint32_t)R * (D * 2 + C * 8));
-            residual_epilogue(sm, acc, R, vec + VC_BO, rank, e24_addr, st_addr, eb[1]);
+            if (tid == 0) mbar_expect_tx(&sm.ebar[1], (uint32_t)(C * (BLK_ST + R * ROW_S)));
+            residual_epilogue(sm, acc, R, vec + VC_BO, rank, sm.stage[xch & 1], e24_addr, eb[1]);
+            ++xch;
             CS_TL();
           }
           mbar_wait_cluster(&sm.ebar[1], (epar >> 1) & 1u); epar ^= 2u;
@@ -646,36 +674,39 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           // ---- FFN1 (128 hidden units, one tile per warp) + bias + ReLU -> exchange 3
           {
             float acc[4];
-            gemv_ldg<NF_W1>(lw + w1, wf, &sm.xn[0][0], XS8, 0, acc);
-            ldg_batch(lw + w2, wf);  // FFN2's first batch: in flight during hand-off 3
+            gemv_ldg<NF_W1, NF_W1, 0, XS8>(lw + w1, wf, &sm.xn[0][0], 0, acc);
+            ldg_batch<FB>(lw + w2, wf);  // FFN2's first batch: in flight during hand-off 3
             CS_TL();
             const int f0 = warp * 16 + g;
             const float b0 = vec[VC_B1 + f0], b1 = vec[VC_B1 + f0 + 8];
-            bf16* hs = reinterpret_cast<bf16*>(sm.stage);
-            hs[(2 * t) * FH + f0] = __float2bfloat16_rn(fmaxf(acc[0] + b0, 0.f));
-            hs[(2 * t + 1) * FH + f0] = __float2bfloat16_rn(fmaxf(acc[1] + b0, 0.f));
-            hs[(2 * t) * FH + f0 + 8] = __float2bfloat16_rn(fmaxf(acc[2] + b1, 0.f));
-            hs[(2 * t + 1) * FH + f0 + 8] = __float2bfloat16_rn(fmaxf(acc[3] + b1, 0.f));
+            bf16* hs = reinterpret_cast<bf16*>(sm.stage[xch & 1]);  // row stride ROW_H bytes
+            hs[(2 * t) * (ROW_H / 2) + f0] = __float2bfloat16_rn(fmaxf(acc[0] + b0, 0.f));
+            hs[(2 * t + 1) * (ROW_H / 2) + f0] = __float2bfloat16_rn(fmaxf(acc[1] + b0, 0.f));
+            hs[(2 * t) * (ROW_H / 2) + f0 + 8] = __float2bfloat16_rn(fmaxf(acc[2] + b1, 0.f));
+            hs[(2 * t + 1) * (ROW_H / 2) + f0 + 8] = __float2bfloat16_rn(fmaxf(acc[3] + b1, 0.f));
+            fence_proxy_async_smem();
             csync();
-            if (tid == 0) mbar_expect_tx(&sm.ebar[2], (uint32_t)R * FF * 2);
-            all_gather<FH * 2 / 16>(sm, e13_addr, HS8 * 2, R, rank, eb[2]);
+            if (tid == 0) mbar_expect_tx(&sm.ebar[2], (uint32_t)(C * R * ROW_H));
+            all_gather(s32(sm.stage[xch & 1]), e13_addr, BLK_H, R * ROW_H, rank, eb[2]);
+            ++xch;
             mbar_wait_cluster(&sm.ebar[2], (epar >> 2) & 1u); epar ^= 4u;
             CS_TL();
           }
           // ---- FFN2 (32 outputs, K = 2048 split over warp pairs) + bias + residual -> exchange 4
           {
             float acc[4];
-            gemv_ldg<NF_W2>(lw + w2, wf, reinterpret_cast<const bf16*>(sm.e13), HS8, (warp >> 1) * 32, acc);
+            gemv_ldg<NF_W2, 8, BLK_H / 2, ROW_H / 2>(lw + w2, wf, reinterpret_cast<const bf16*>(sm.e13), (warp >> 1) * 32, acc);
             // next unit's first batch (QKV of the next layer, or the head) in flight during hand-off 4 and LayerNorm 2
             if (layer + 1 < c.n_layer) {
               lw += (size_t)C * LAYER_BYTES / 16;
-              if (warp < NW_QKV) ldg_batch(lw + wq, wf);
+              if (warp < NW_QKV) ldg_batch<FB>(lw + wq, wf);
             } else if (warp < HEAD_TILES) {
-              ldg_batch(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf);
+              ldg_batch<FB>(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf);
             }
             CS_TL();
-            if (tid == 0) mbar_expect_tx(&sm.ebar[3], (uint32_t)R * (D * 2 + C * 8));
-            residual_epilogue(sm, acc, R, vec + VC_B2, rank, e24_addr, st_addr, eb[3]);
+            if (tid == 0) mbar_expect_tx(&sm.ebar[3], (uint32_t)(C * (BLK_ST + R * ROW_S)));
+            residual_epilogue(sm, acc, R, vec + VC_B2, rank, sm.stage[xch & 1], e24_addr, eb[3]);
+            ++xch;
           }
           mbar_wait_cluster(&sm.ebar[3], (epar >> 3) & 1u); epar ^= 8u;
           CS_TL();
@@ -690,8 +721,8 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
         {
           float acc[4];
           if (warp < HEAD_TILES) {
-            gemv_ldg<NF_HEAD>(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf,
-                              &sm.xn[0][0], XS8, 0, acc);
+            gemv_ldg<NF_HEAD, NF_HEAD, 0, XS8>(reinterpret_cast<const uint4*>(hstream + (size_t)rank * HEAD_BYTES) + (size_t)warp * NF_HEAD * 32 + lane, wf,
+                                               &sm.xn[0][0], 0, acc);
             const int f0 = ((int)rank + C * warp) * 16 + g;
             const int n0 = 2 * t, n1 = 2 * t + 1;
             if (n0 < R) {
