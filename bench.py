@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_b32", choices=sorted(WORKLOADS))
-    ap.add_argument("--decode-mode", type=int, default=1)
+    ap.add_argument("--decode-mode", type=int, default=5, help="5 = auto (cluster-stream kernel when the batch fits, else grid-wide phases)")
     ap.add_argument("--cpu-steps", type=int, default=24, help="decode steps of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -302,10 +302,11 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         achieved = bytes_alg / (dec_ms / 1000.0) / 1e9  # rank 0's persistent decode kernel
+        st_mode = eng.stats()["decode_mode"]
         traffic = None  # dram bytes of the same launch from the committed ncu --set full capture (profiles/)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr.get("workload") == name and args.decode_mode == 1:
+            if tr.get("workload") == name and int(tr.get("decode_mode", 1)) == int(st_mode):
                 traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
         except Exception:
             pass
@@ -323,7 +324,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {
-                "kernel": "k_decode_persistent" if args.decode_mode == 1 else "decode step graph (122 kernels)",
+                "kernel": {4: "k_decode_cluster", 1: "k_decode_persistent"}.get(int(st_mode), "decode step graph"),
+                "decode_mode": int(st_mode),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_alg / args.steps,

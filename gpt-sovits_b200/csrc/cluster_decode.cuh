@@ -9,13 +9,15 @@
 // C = 16 CTAs (one GPC) owns a few sequences end to end:
 //   * CTA `rank` of a cluster is attention head `rank` and owns 1/16 of every weight matrix (32 q/k/v features, 32
 //     O-proj outputs, 128 FFN hidden units, 32 FFN2 outputs).  Its weights are ONE private, consumption-ordered byte
-//     stream (393 KB per layer, packed once by k_pack_stream, mma.m16n8k16 A-fragment order, contiguous per warp).  A
-//     prefetch lane pulls the stream into L2 two layers ahead (cp.async.bulk.prefetch.L2); the consumer warps read their
-//     fragments straight from L2 into registers with 128-bit loads, 8 in flight per lane, the first batch of the next
-//     matrix issued BEFORE the hand-off wait that precedes it.  (Weights never touch shared memory: a TMA ring doubled
-//     the shared-memory traffic and bounded the GEMVs, see DESIGN.md.)
+//     stream (393 KB per layer, packed once by k_pack_stream, mma.m16n8k16 A-fragment order, contiguous per warp).  The
+//     warps pull the stream into L2 two layers ahead (cp.async.bulk.prefetch.L2) and read their fragments straight from
+//     L2 into registers with 128-bit loads, 16 in flight per lane, the first batch of the next matrix issued BEFORE the
+//     hand-off wait that precedes it.  (Weights never touch shared memory: a TMA ring doubled the shared-memory traffic
+//     and bounded the GEMVs, see DESIGN.md.)
 //   * The K/V pages of the head (one contiguous 16 KB block per 128 positions: common.cuh kv_row_off) stream through an
-//     8 x 16 KB shared-memory ring fed by TMA bulk copies (one copy per page), running ahead across layers.
+//     8 x 16 KB shared-memory ring fed by TMA bulk copies (one copy per page), running ahead across layers.  Ring slot i
+//     belongs to warp i: the warp consumes a page on the tensor cores and immediately issues the copy of the next page
+//     that maps to its slot, so there is no producer warp, no "empty" barrier and all 8 warps keep 255 registers.
 //   * The four hand-offs of a layer (attention out, residual sum 1, FFN hidden, residual sum 2) are all-gathers through
 //     DISTRIBUTED SHARED MEMORY: st.async writes 16-byte pieces into every peer's buffer and completes bytes on the
 //     peer's mbarrier, so data and "ready" signal travel together (~0.3 us per hand-off instead of a grid barrier).
@@ -31,11 +33,10 @@ namespace cs {
 
 constexpr int C = 16;            // CTAs per cluster (= heads)
 constexpr int RMAX = 8;          // sequences per cluster (one MMA n-tile)
-constexpr int NCW = 8;           // consumer warps
+constexpr int NCW = 8;           // warps per CTA
 constexpr int SLOT = 16384;      // K/V ring slot: one (page, head) block = K 8 KB | V 8 KB
 constexpr int NSLOT = 8;
-constexpr int NPW = 2;           // producer warps: K/V TMA ring; weight L2 prefetch + the layer-vector ring
-constexpr int NTC = (NCW + NPW) * 32;
+constexpr int NTC = NCW * 32;
 constexpr int HD = D / C;        // 32: q/k/v features, O-proj outputs, FFN2 outputs per CTA
 constexpr int FH = FF / C;       // 128 FFN hidden units per CTA
 // vector chunk (fp32): biases of this CTA's slices, then the four LayerNorm vectors in full (every CTA normalises whole rows)
@@ -80,12 +81,9 @@ struct __align__(128) Smem {
   int row_slot[RMAX], row_pos[RMAX];
   long long row_kvoff[RMAX];
   alignas(16) float vec[2][VC_FLOATS];  // the layer's vectors (biases of the own slices, LayerNorm gamma / beta): 2-deep ring of its own
-  unsigned long long full[NSLOT], empty[NSLOT], vfull[2], vempty[2], ebar[4], cbar;
-  volatile int stop;
-  volatile unsigned consumed, vconsumed;
-  volatile int step_seq;  // consumers -> producers: steps whose row descriptors (row_pos, pt, n_rows) are in place
-  volatile int unit_seq;  // consumers -> prefetch lane: (layer | head) units started so far
-  volatile int n_rows;
+  int row_npg[RMAX];                  // cached pages per sequence this step
+  unsigned short pmap[RMAX * 32];     // page q of a layer (consumption order) -> (sequence << 8) | page
+  unsigned long long full[NSLOT], vfull[2], ebar[4], cbar;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------------
@@ -218,6 +216,12 @@ __global__ void k_pack_stream(unsigned char* __restrict__ wstream, bf16* __restr
   }
 }
 
+// One bulk-prefetch instruction costs the issuing warp ~0.25 us (measured), whatever its size: keep them few and big, and
+// issue them where the warp is about to wait anyway (in front of a hand-off wait).
+__device__ __forceinline__ void l2_prefetch(const unsigned char* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- consumer-side building blocks -------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ring_slot(unsigned i) { return i & (NSLOT - 1); }
 __device__ __forceinline__ unsigned ring_par(unsigned i) { return (i >> 3) & 1u; }
@@ -329,96 +333,184 @@ __device__ __forceinline__ void residual_epilogue(Smem& sm, const float (&acc)[4
   all_gather(s32(stage), e24_addr, BLK_Y, BLK_ST + R * ROW_S, rank, ebar);
 }
 
-// Single-query attention of head `rank` for the cluster's R sequences.  The cached positions [0, pos) arrive through the
-// ring, one 128-position page per slot: K rows at byte i*64, V rows at 8192 + i*64.  Position `pos` (this step's token)
-// comes from shared memory.  A page is processed by ONE warp (ring chunk i -> warp i % 8 = ring slot i % 8): a quad of lanes
-// owns positions quad, quad+8, ... (4 x 16 B = the head's 32 dims each), scores four of them, then folds them into its
-// online-softmax state in one update; the quads of a warp, then the warps are merged in a fixed order.
-__device__ __forceinline__ float dot8(const float (&q)[8], const uint4& k) {
-  return q[0] * bf_lo(k.x) + q[1] * bf_hi(k.x) + q[2] * bf_lo(k.y) + q[3] * bf_hi(k.y) + q[4] * bf_lo(k.z) + q[5] * bf_hi(k.z) +
-         q[6] * bf_lo(k.w) + q[7] * bf_hi(k.w);
+// Single-query attention of head `rank` for the cluster's R sequences, on the tensor cores.
+// The cached positions [0, pos) arrive through the ring, one 128-position page per slot: K rows at byte i*64, V rows at
+// 8192 + i*64, the four 16-byte chunks of a row XOR-swizzled by ((i >> 1) & 3) (common.cuh), so ldmatrix is conflict free.
+// A page is processed by ONE warp (ring chunk i -> warp i % 8 = ring slot i % 8):
+//   scores   S[128 pos x 8] = K[128 x 32] . Qt[32 x 8]   (m16n8k16, A = K tile via ldmatrix; the 8 columns of Qt alternate
+//            bf16 hi / lo halves of the fp32 query, so c0 + c1 of every lane is the score at fp32-query precision)
+//   softmax  online, state (m, l) per warp; probabilities rounded to bf16 (and summed rounded: l matches the PV operand)
+//   output   O[32 dims x 8] = Vt[32 x 128] . P[128 x 8]   (A = V tile via ldmatrix.trans, all columns of P identical)
+// This step's token (k, v still in shared memory) joins in the final merge of the warps' partial states.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint4& r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
 }
-__device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) {
-  acc[0] += p * bf_lo(v.x); acc[1] += p * bf_hi(v.x); acc[2] += p * bf_lo(v.y); acc[3] += p * bf_hi(v.y);
-  acc[4] += p * bf_lo(v.z); acc[5] += p * bf_hi(v.z); acc[6] += p * bf_lo(v.w); acc[7] += p * bf_hi(v.w);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint4& r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
 }
-__device__ __forceinline__ void attention_rows(Smem& sm, unsigned& cons, int R, unsigned char* stage) {
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// round-to-nearest-even to bf16 with integer ops (finite inputs; the conversion instruction runs on the quarter-rate pipe
+// that the exponentials already saturate)
+__device__ __forceinline__ float bf16_round_fast(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+// two floats that are already bf16-representable -> packed bf16x2 (lo = a, hi = b)
+__device__ __forceinline__ uint32_t pack_bf2_exact(float a, float b) { return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632); }
+
+// The K/V pages a CTA reads in one step, in consumption order: layer-major, then sequence, then page.  Page q of the step
+// has ring index base + q; ring index i lives in slot i % 8, which belongs to warp i % 8.
+struct KvStream { unsigned base; int total, ptot; };  // ring index of the step's first page; pages per step; pages per layer
+// lane 0 of the owning warp: start the TMA copy of ring index idx (= page `rem` of layer `layer`, rem < ptot) into its slot.
+// sm.pmap[rem] = (sequence << 8) | page was filled by the step prologue.
+__device__ __forceinline__ void kv_issue(const Ctx& c, Smem& sm, unsigned idx, int layer, int rem, uint32_t rank) {
+  const int e = sm.pmap[rem], n = e >> 8, pg = e & 0xFF;
+  const int pos = sm.row_pos[n];
+  const uint32_t bytes = (uint32_t)(PAGE * DH * 2 + min(PAGE, pos - pg * PAGE) * DH * 2);  // K block + the valid V rows
+  const bf16* src = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE + (size_t)sm.pt[n][pg] * KV_PAGE_STRIDE;
+  const unsigned slot = ring_slot(idx);
+  // (the slot's previous page was read by this warp's ldmatrix, complete before the MMAs that consumed it were issued;
+  //  the generic -> async proxy fence for K/V rows appended in earlier steps is executed once per step by the caller)
+  mbar_expect_tx(&sm.full[slot], bytes);
+  bulk_load(sm.ring[slot], src, bytes, &sm.full[slot]);
+}
+
+__device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvStream& ks, uint32_t rank, int layer, unsigned& cons,
+                                               int R, unsigned char* stage) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = lane >> 2, part = lane & 3;
-  unsigned j = cons;  // ring index of the next page (same order as the producer: sequences, then pages)
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;  // ldmatrix: lane supplies row r8 of 8x8 matrix mi
+  // K tile (16 pos x 16 dims) as A: matrices (pos 0-7 | 8-15) x (dims 0-7 | 8-15) in the order a0..a3
+  const int k_pos = (mi & 1) * 8 + r8, k_chunk = mi >> 1;   // + tile*16 positions, + kb*2 chunks
+  // V tile as A = Vt (16 dims x 16 pos): a0 = (dims 0-7, pos 0-7), a1 = (dims 8-15, pos 0-7), a2 = (dims 0-7, pos 8-15), a3
+  const int v_pos = (mi >> 1) * 8 + r8, v_chunk = mi & 1;   // + kb*16 positions, + mt*2 chunks
+  unsigned j = cons;  // ring index of the next page (KvStream order: sequences, then pages)
   for (int n = 0; n < R; ++n) {
     const int pos = sm.row_pos[n];
-    const int npg = (pos + PAGE - 1) >> PAGE_SHIFT;
-    // ring chunk i (a whole page) belongs to warp i % 8 = the warp that always reads ring slot i % 8: every warp sees the
-    // phases of its slot strictly in order (an mbarrier parity wait must never run a phase ahead), pages are spread evenly
+    const int npg = sm.row_npg[n];
+    // ring index i (a whole page) belongs to warp i % 8, the owner of ring slot i % 8: every warp sees the phases of its
+    // slot strictly in order (an mbarrier parity wait must never run a phase ahead) and pages are spread evenly
     const int first = (warp - (int)j) & (NCW - 1);
     if (first < npg) {
-      float qv[8];
+      // B fragments of the query: k = dims 2t,2t+1 (+8), column g: even -> bf16 hi part, odd -> lo part
+      uint32_t qb[2][2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) qv[i] = sm.q[n][part * 8 + i];
-      float m = -INFINITY, l = 0.f, acc[8];
+      for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int h = 0; h < 2; ++h) {
+          const float q0 = sm.q[n][kb * 16 + h * 8 + 2 * t], q1 = sm.q[n][kb * 16 + h * 8 + 2 * t + 1];
+          const float h0 = bf16_round(q0), h1 = bf16_round(q1);
+          qb[kb][h] = (g & 1) ? pack_bf2(q0 - h0, q1 - h1) : pack_bf2(h0, h1);
+        }
+      float m = -INFINITY, l = 0.f;
+      float o[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[mt][i] = 0.f;
       for (int pg = first; pg < npg; pg += NCW) {
         const int np = min(PAGE, pos - pg * PAGE);
+        const int ntile = (np + 15) >> 4;
         const unsigned slot = ring_slot(j + pg);
         mbar_wait(&sm.full[slot], ring_par(j + pg));
-        const unsigned char* kb = sm.ring[slot] + part * 16;
-        for (int u0 = 0; u0 * 8 < np; u0 += 4) {  // 4 positions per quad per round: 32 positions per warp round
-          uint4 kk[4], vv[4];
-          bool ok[4];
-          float sc[4];
+        const uint32_t base = s32(sm.ring[slot]);
+        float sc[8][2];
+        float mx = -INFINITY;
+        {
+          // all K fragments first (independent ldmatrix), then the MMAs tile-interleaved: consecutive MMAs are independent
+          uint4 ka[8][2];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = (u0 + u) * 8 + quad;
-            ok[u] = i < np;
-            const int ic = ok[u] ? i : 0;
-            kk[u] = *reinterpret_cast<const uint4*>(kb + ic * 64);
-            vv[u] = *reinterpret_cast<const uint4*>(kb + 8192 + ic * 64);
+          for (int pt = 0; pt < 8; ++pt) {
+            const int p = pt * 16 + k_pos;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+              if (pt < ntile) ldsm_x4(base + p * 64 + (((kb * 2 + k_chunk) ^ ((p >> 1) & 3)) << 4), ka[pt][kb]);
+          }
+          float c[8][4];
+#pragma unroll
+          for (int pt = 0; pt < 8; ++pt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[pt][i] = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int pt = 0; pt < 8; ++pt)
+              if (pt < ntile) mma_bf16_16816(c[pt], ka[pt][kb], qb[kb][0], qb[kb][1]);
+#pragma unroll
+          for (int pt = 0; pt < 8; ++pt) {
+            sc[pt][0] = (pt * 16 + g < np) ? c[pt][0] + c[pt][1] : -INFINITY;
+            sc[pt][1] = (pt * 16 + 8 + g < np) ? c[pt][2] + c[pt][3] : -INFINITY;
+            mx = fmaxf(mx, fmaxf(sc[pt][0], sc[pt][1]));
+          }
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float mn = fmaxf(m, mx);  // finite: np >= 1
+        const float corr = fast_exp2(m - mn);
+        m = mn;
+        float ls = 0.f;
+#pragma unroll
+        for (int pt = 0; pt < 8; ++pt) {
+          sc[pt][0] = bf16_round_fast(fast_exp2(sc[pt][0] - mn));
+          sc[pt][1] = bf16_round_fast(fast_exp2(sc[pt][1] - mn));
+          ls += sc[pt][0] + sc[pt][1];
+        }
+        l = l * corr + ls;  // this lane's positions only (g, g+8 of every tile); the quads are summed once per sequence
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[mt][i] *= corr;
+        {
+          // B fragments of P: positions 16kb + (2t, 2t+1 | 2t+8, 2t+9) are held by the quads g' = 2t and 2t+1
+          uint32_t pb[8][2];
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const float pa = __shfl_sync(0xffffffffu, sc[kb][0], 8 * t + t), pq = __shfl_sync(0xffffffffu, sc[kb][0], 8 * t + 4 + t);
+            const float pc = __shfl_sync(0xffffffffu, sc[kb][1], 8 * t + t), pd = __shfl_sync(0xffffffffu, sc[kb][1], 8 * t + 4 + t);
+            pb[kb][0] = pack_bf2_exact(pa, pq); pb[kb][1] = pack_bf2_exact(pc, pd);
+          }
+          float o2[2][4];  // second accumulator chain per output tile (odd position blocks): shorter dependent MMA chains
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[mt][i] = 0.f;
+#pragma unroll
+          for (int k2 = 0; k2 < 8; k2 += 2) {
+            uint4 va[2][2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int p = (k2 + q) * 16 + v_pos;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+                if (k2 + q < ntile) ldsm_x4_t(base + 8192 + p * 64 + (((mt * 2 + v_chunk) ^ ((p >> 1) & 3)) << 4), va[q][mt]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (k2 < ntile) mma_bf16_16816(o[mt], va[0][mt], pb[k2][0], pb[k2][1]);
+              if (k2 + 1 < ntile) mma_bf16_16816(o2[mt], va[1][mt], pb[k2 + 1][0], pb[k2 + 1][1]);
+            }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) sc[u] = dot8(qv, kk[u]);
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
-          float mn = m;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) if (ok[u]) mn = fmaxf(mn, sc[u]);
-          if (ok[0]) {  // ok[u] implies ok[0]
-            const float corr = fast_exp2(m - mn);
-            float e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) e[u] = ok[u] ? fast_exp2(sc[u] - mn) : 0.f;
-            m = mn;
-            l = l * corr + (e[0] + e[1]) + (e[2] + e[3]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] *= corr;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) axpy8(acc, e[u], vv[u]);
-          }
+            for (int i = 0; i < 4; ++i) o[mt][i] += o2[mt][i];
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[slot]);
-      }
-      // merge the 8 quads of the warp (fixed xor tree: deterministic)
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
-        const float mn = fmaxf(m, mo);
-        const float ca = (m == -INFINITY) ? 0.f : fast_exp2(m - mn), cb = (mo == -INFINITY) ? 0.f : fast_exp2(mo - mn);
-        l = l * ca + lo * cb;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ao = __shfl_xor_sync(0xffffffffu, acc[i], o);
-          acc[i] = acc[i] * ca + ao * cb;
+        if (lane == 0) {  // the slot is free again: fetch the next page that maps to it (8 pages on, possibly in a later layer)
+          int nl = layer, nr = (int)(j + pg - cons) + NSLOT;  // page number inside the layer
+          while (nr >= ks.ptot) { nr -= ks.ptot; ++nl; }
+          if (nl < c.n_layer) kv_issue(c, sm, j + pg + NSLOT, nl, nr, rank);
         }
-        m = mn;
       }
-      if (quad == 0) {
-        if (part == 0) { sm.am[warp][n] = m; sm.al[warp][n] = l; }
+      // the quads hold disjoint positions: sum l over g (every column of O already covers all positions of the pages)
+      l += __shfl_xor_sync(0xffffffffu, l, 4);
+      l += __shfl_xor_sync(0xffffffffu, l, 8);
+      l += __shfl_xor_sync(0xffffffffu, l, 16);
+      if (t == 0) {
+        if (g == 0) { sm.am[warp][n] = m; sm.al[warp][n] = l; }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sm.aacc[warp][n][part * 8 + i] = acc[i];
+        for (int mt = 0; mt < 2; ++mt) { sm.aacc[warp][n][mt * 16 + g] = o[mt][0]; sm.aacc[warp][n][mt * 16 + 8 + g] = o[mt][2]; }
       }
     } else if (lane == 0) {
       sm.am[warp][n] = -INFINITY;  // no page of this sequence for this warp
@@ -478,9 +570,6 @@ struct GridBar {
   }
 };
 
-__device__ __forceinline__ void l2_prefetch(const unsigned char* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 
 // =====================================================================================================================
 __global__ void __launch_bounds__(NTC, 1)
@@ -490,77 +579,39 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), cid = cluster_idx(), ncl = n_clusters();
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }  // a page is consumed by ONE warp
+    for (int s = 0; s < NSLOT; ++s) mbar_init(&sm.full[s], 1);
     for (int k = 0; k < 4; ++k) mbar_init(&sm.ebar[k], 1);
-    for (int k = 0; k < 2; ++k) { mbar_init(&sm.vfull[k], 1); mbar_init(&sm.vempty[k], NCW); }
+    for (int k = 0; k < 2; ++k) mbar_init(&sm.vfull[k], 1);
     mbar_init(&sm.cbar, C);
-    sm.stop = 0; sm.consumed = 0; sm.vconsumed = 0; sm.step_seq = 0; sm.unit_seq = 0; sm.n_rows = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // stale ring bytes are multiplied by zero probabilities in the PV MMAs: they must be finite
+  for (int i = tid; i < NSLOT * SLOT / 16; i += NTC) reinterpret_cast<uint4*>(sm.ring)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   cluster_sync_all();
   const int units_per_step = c.n_layer + 1;  // 24 layers + the head
 
-  if (warp == NCW) {
-    // ---------------- producer 1: the K/V pages of head `rank` of this cluster's sequences, through the ring --------------
-    if (lane == 0) {
-      unsigned issued = 0;
-      int steps_done = 0;
-      bool run = true;
-      while (run) {
-        while (sm.step_seq <= steps_done) { if (sm.stop) { run = false; break; } }  // rows of the step known?
-        if (!run) break;
-        asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows appended by generic-proxy stores in earlier steps
-        const int R = sm.n_rows;
-        for (int layer = 0; layer < c.n_layer && run; ++layer) {
-          const bf16* kl = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE;
-          for (int n = 0; n < R && run; ++n) {
-            const int pos = sm.row_pos[n];
-            for (int p0 = 0; p0 < pos; p0 += PAGE) {
-              const unsigned slot = ring_slot(issued), par = ring_par(issued) ^ 1u;
-              while (!mbar_try(&sm.empty[slot], par)) { if (sm.stop) { run = false; break; } }
-              if (!run) break;
-              const uint32_t bytes = (uint32_t)(PAGE * DH * 2 + min(PAGE, pos - p0) * DH * 2);  // K block + the valid V rows
-              mbar_expect_tx(&sm.full[slot], bytes);
-              bulk_load(sm.ring[slot], kl + (size_t)sm.pt[n][p0 >> PAGE_SHIFT] * KV_PAGE_STRIDE, bytes, &sm.full[slot]);
-              ++issued;
-            }
-          }
-        }
-        ++steps_done;
-      }
-      // drain: every copy that was issued but never consumed must land before the CTA may exit
-      for (unsigned i = sm.consumed; i < issued; ++i) mbar_wait(&sm.full[ring_slot(i)], ring_par(i));
-    }
-  } else if (warp == NCW + 1) {
-    // ---------------- producer 2: weight stream -> L2 two units ahead; the layer vectors -> their own 2-deep ring ----------
-    if (lane == 0) {
-      unsigned vissued = 0;
-      bool run = true;
-      for (int u = 0; run; ++u) {  // unit u = layer (u % units_per_step), or the head
-        while (sm.unit_seq + 2 < u) { if (sm.stop) { run = false; break; } }
-        if (!run) break;
-        const int layer = u % units_per_step;
-        if (layer < c.n_layer) {
-          const unsigned char* base = wstream + ((size_t)layer * C + rank) * LAYER_BYTES;
-          for (int o = 0; o < LAYER_BYTES; o += 32768) l2_prefetch(base + o, (uint32_t)min(32768, LAYER_BYTES - o));
-          const unsigned vs = vissued & 1u, vp = ((vissued >> 1) & 1u) ^ 1u;
-          while (!mbar_try(&sm.vempty[vs], vp)) { if (sm.stop) { run = false; break; } }
-          if (!run) break;
-          mbar_expect_tx(&sm.vfull[vs], CH_VEC);
-          bulk_load(sm.vec[vs], base + OFFS_VEC, CH_VEC, &sm.vfull[vs]);
-          ++vissued;
-        } else {
-          const unsigned char* hb = hstream + (size_t)rank * HEAD_BYTES;
-          for (int o = 0; o < HEAD_BYTES; o += 32768) l2_prefetch(hb + o, (uint32_t)min(32768, HEAD_BYTES - o));
-        }
-      }
-      for (unsigned i = sm.vconsumed; i < vissued; ++i) mbar_wait(&sm.vfull[i & 1u], (i >> 1) & 1u);
-    }
-  } else {
-    // ---------------- consumers ------------------------------------------------------------------------------------------
+  // weight stream -> L2: unit u = layer (u % units_per_step) or the head; every warp pulls its eighth of unit u, two units
+  // ahead of the compute.  The units of the next step are the same bytes, so running ahead is always legal.
+  auto prefetch_unit = [&](int u) {
+    if (lane != 0) return;
+    const int layer = u % units_per_step;
+    if (layer < c.n_layer) l2_prefetch(wstream + ((size_t)layer * C + rank) * LAYER_BYTES + (size_t)warp * (LAYER_BYTES / NCW), LAYER_BYTES / NCW);
+    else l2_prefetch(hstream + (size_t)rank * HEAD_BYTES + (size_t)warp * (HEAD_BYTES / NCW), HEAD_BYTES / NCW);
+  };
+  // the layer vectors: 2-deep ring fed by TMA; layer number v (counted over all steps) uses buffer v & 1
+  auto vec_issue = [&](unsigned v) {
+    if (tid != 0) return;
+    // (the buffer's previous readers, two layers back, are separated from this copy by several CTA barriers)
+    mbar_expect_tx(&sm.vfull[v & 1u], CH_VEC);
+    bulk_load(sm.vec[v & 1u], wstream + ((size_t)(v % (unsigned)c.n_layer) * C + rank) * LAYER_BYTES + OFFS_VEC, CH_VEC, &sm.vfull[v & 1u]);
+  };
+  prefetch_unit(0);
+  prefetch_unit(1);
+  vec_issue(0);
+  {
     GridBar gbar{c.bar, c.abort_flag, 0u, gridDim.x};
-    unsigned cons = 0, vcons = 0;
+    unsigned cons = 0, vcons = 0;  // ring index of the next K/V page; layers consumed so far
     uint32_t epar = 0;  // bit k = parity of exchange barrier k
     uint32_t cpar = 0;
     const uint32_t e13_addr = s32(sm.e13), e24_addr = s32(sm.e24);
@@ -592,6 +643,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           sm.row_slot[tid] = ld_cg_i(c.row_slot + r);
           sm.row_pos[tid] = ld_cg_i(c.row_pos + r);
           sm.row_kvoff[tid] = __ldcg(c.row_kvoff + r);
+          sm.row_npg[tid] = (sm.row_pos[tid] + PAGE - 1) >> PAGE_SHIFT;
         }
         csync();
         for (int i = tid; i < R * 32; i += NCW * 32) {
@@ -611,10 +663,26 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           sm.xres[n][lane] = ld_cg_f(xr + rank * HD + lane);
         }
         csync();
-        if (tid == 0) { sm.n_rows = R; __threadfence_block(); sm.step_seq = sm.step_seq + 1; }  // the K/V producer may list this step
+        // ---- this step's K/V page stream; every warp starts the copy of the first page that maps to its ring slot
+        KvStream ks;
+        ks.base = cons; ks.ptot = 0;
+        for (int n = 0; n < R; ++n) {
+          const int npg = sm.row_npg[n];
+          for (int pg = tid; pg < npg; pg += NCW * 32) sm.pmap[ks.ptot + pg] = (unsigned short)((n << 8) | pg);
+          ks.ptot += npg;
+        }
+        ks.total = ks.ptot * c.n_layer;
+        csync();
+        if (lane == 0 && ks.ptot > 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows appended by ordinary stores in earlier steps -> TMA reads
+          int nl = 0, nr = (warp - cons) & (NSLOT - 1);  // the first page of the step that maps to this warp's slot
+          const unsigned first = cons + nr;
+          while (nr >= ks.ptot) { nr -= ks.ptot; ++nl; }
+          if (nl < c.n_layer) kv_issue(c, sm, first, nl, nr, rank);
+        }
         CS_TL();
         for (int layer = 0; layer < c.n_layer; ++layer) {
-          if (tid == 0) sm.unit_seq = ++unit;
+          ++unit;
           // ---- the layer's vectors (own 2-deep ring; normally long landed)
           const unsigned vslot = vcons & 1u;
           mbar_wait(&sm.vfull[vslot], (vcons >> 1) & 1u);
@@ -640,19 +708,20 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
                 const bf16 h00 = __float2bfloat16_rn(v00), h01 = __float2bfloat16_rn(v01), h10 = __float2bfloat16_rn(v10),
                            h11 = __float2bfloat16_rn(v11);
                 dst[n0][f0] = h00; dst[n1][f0] = h01; dst[n0][f0 + 8] = h10; dst[n1][f0 + 8] = h11;
-                if (n0 < R) { pool[sm.row_kvoff[n0] + f0] = h00; pool[sm.row_kvoff[n0] + f0 + 8] = h10; }
-                if (n1 < R) { pool[sm.row_kvoff[n1] + f0] = h01; pool[sm.row_kvoff[n1] + f0 + 8] = h11; }
+                if (n0 < R) { const long long o = sm.row_kvoff[n0]; pool[o + kv_feat(o, f0)] = h00; pool[o + kv_feat(o, f0 + 8)] = h10; }
+                if (n1 < R) { const long long o = sm.row_kvoff[n1]; pool[o + kv_feat(o, f0)] = h01; pool[o + kv_feat(o, f0 + 8)] = h11; }
               }
             }
             csync();
           }
           // ---- attention, then hand the head's output to every peer (exchange 1)
           CS_TL();
-          attention_rows(sm, cons, R, sm.stage[xch & 1]);
+          attention_rows(c, sm, ks, rank, layer, cons, R, sm.stage[xch & 1]);
           CS_TL();
           if (tid == 0) mbar_expect_tx(&sm.ebar[0], (uint32_t)(C * R * ROW_S));
           all_gather(s32(sm.stage[xch & 1]), e13_addr, BLK_A, R * ROW_S, rank, eb[0]);
           ++xch;
+          prefetch_unit(unit + 1);  // weights two units ahead -> L2; issued where the warp is about to wait anyway
           mbar_wait_cluster(&sm.ebar[0], (epar >> 0) & 1u); epar ^= 1u;
           CS_TL();
           // ---- O-projection (32 outputs, split-K over warp pairs) + bias + residual -> exchange 2
@@ -666,6 +735,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
             ++xch;
             CS_TL();
           }
+          vec_issue(vcons);  // the next layer's vectors (its buffer was last read two layers ago)
           mbar_wait_cluster(&sm.ebar[1], (epar >> 1) & 1u); epar ^= 2u;
           CS_TL();
           layer_norm_rows(sm, R, rank, vec + VC_G1, vec + VC_BE1);
@@ -711,13 +781,12 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           mbar_wait_cluster(&sm.ebar[3], (epar >> 3) & 1u); epar ^= 8u;
           CS_TL();
           layer_norm_rows(sm, R, rank, vec + VC_G2, vec + VC_BE2);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.vempty[vslot]);  // done with the layer's vectors
           csync();
           CS_TL();
         }
         // ---- head: vocabulary tiles rank, rank+16, ... (warps 0..4) -> logits in global memory
-        if (tid == 0) sm.unit_seq = ++unit;
+        ++unit;
+        prefetch_unit(unit + 1);
         {
           float acc[4];
           if (warp < HEAD_TILES) {
@@ -754,7 +823,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
       CS_TL();
     }
 #undef CS_TL
-    if (tid == 0) { sm.consumed = cons; sm.vconsumed = vcons; __threadfence_block(); sm.stop = 1; }
+    if (tid == 0) mbar_wait(&sm.vfull[vcons & 1u], (vcons >> 1) & 1u);  // the one outstanding vector copy must land before exit
   }
   __syncwarp();
   cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory

@@ -47,7 +47,14 @@ constexpr int KV_HEAD_STRIDE = 2 * PAGE * DH;       // elements between heads in
 constexpr int KV_PAGE_STRIDE = NH * KV_HEAD_STRIDE; // elements per page (all heads, K and V)
 constexpr int KV_V_OFF = PAGE * DH;                 // V block behind the K block
 __host__ __device__ constexpr long long kv_row_off(long long page, int pos_in_page) { return page * KV_PAGE_STRIDE + (long long)pos_in_page * DH; }
-__host__ __device__ constexpr int kv_feat(int f) { return (f >> 5) * KV_HEAD_STRIDE + (f & (DH - 1)); }
+// A position's 64-byte head row is stored with its four 16-byte chunks XOR-swizzled by ((position >> 1) & 3): eight
+// consecutive positions x one logical chunk then fall into eight distinct shared-memory bank groups, so ldmatrix reads of a
+// page that a bulk copy dropped into shared memory verbatim are conflict free (cluster_decode.cuh).
+// kv_feat(kvoff, f): element offset of feature f = head*32 + dim relative to the row's kvoff (which encodes the position).
+__host__ __device__ constexpr int kv_swz_of(long long kvoff) { return (int)((kvoff >> 6) & 3); }  // (pos_in_page >> 1) & 3
+__host__ __device__ constexpr int kv_feat(long long kvoff, int f) {
+  return (f >> 5) * KV_HEAD_STRIDE + (((((f >> 3) & 3) ^ kv_swz_of(kvoff))) << 3) + (f & 7);
+}
 
 constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
 

@@ -95,7 +95,7 @@ struct t2s_engine {
   int n_logits_rec = 0;
   long long* timeline = nullptr;
   int tl_step = 0, tl_slots = 0;
-  int decode_mode = 1, prefill_gemm = 0, num_ctas = 0, check_steps = 16, tc_decode_min_batch = 160;
+  int decode_mode = 5, prefill_gemm = 0, num_ctas = 0, check_steps = 16, tc_decode_min_batch = 160;
   int graph_mode = -1;
   bool tc_ok = false;
   DevBuf xf, xb;  // tcgen05 prefill path: LayerNorm'ed rows (fp32 residual + bf16 GEMM operand)
@@ -365,7 +365,7 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
 extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
-    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 4) return fail("decode mode must be 0 .. 4"); e->decode_mode = (int)v; break;
+    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 5) return fail("decode mode must be 0 .. 5"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM:
       if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
       if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
@@ -620,7 +620,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>(); c.logits = e->logits.as<float>();
   c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
   c.attn_desc = e->attn_desc.as<int>();
-  c.attn_ctas = (e->decode_mode == 1 && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
+  c.attn_ctas = ((e->decode_mode == 1 || e->decode_mode == 5) && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
 
   c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
   c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
@@ -734,6 +734,10 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   CK(cudaEventRecord(e->ev0, s));
   if (n_active > 0 && budget > 0) {
     int mode = e->decode_mode;
+    if (mode == 5) {  // auto: the cluster-stream kernel whenever the batch fits its 16-CTA clusters, else the grid-wide phases
+      const bool fits = e->max_clusters >= 1 && e->B <= e->max_clusters * cs::RMAX && e->cd.max_pages <= 32;
+      mode = fits ? 4 : 1;
+    }
     if (mode == 1 && e->tc_ok && e->tc_decode_min_batch > 0 && e->B >= e->tc_decode_min_batch) mode = 3;
     if (mode == 3 && !e->tc_ok) return fail("t2s_decode: tcgen05 decode needs the TMA descriptor entry point");
     if (mode == 4) {

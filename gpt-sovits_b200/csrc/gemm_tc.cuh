@@ -224,7 +224,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           for (int j = 0; j < 4; ++j)
             o[j] = make_float4(x[4 * j] * QSCALE, x[4 * j + 1] * QSCALE, x[4 * j + 2] * QSCALE, x[4 * j + 3] * QSCALE);
         } else {
-          store_bf16x16((f0 < 2 * D ? ep.kpool + kv_feat(f0 - D) : ep.vpool + kv_feat(f0 - 2 * D)) + ep.layer_off + (size_t)kvo, x);
+          {  // 16 features = two 16-byte chunks of one head row; chunks are swizzled by position (common.cuh kv_feat)
+            const int fk = (f0 < 2 * D) ? f0 - D : f0 - 2 * D;
+            bf16* base = (f0 < 2 * D ? ep.kpool : ep.vpool) + ep.layer_off + (size_t)kvo;
+            *reinterpret_cast<uint4*>(base + kv_feat(kvo, fk)) = make_uint4(pack_bf2(x[0], x[1]), pack_bf2(x[2], x[3]), pack_bf2(x[4], x[5]), pack_bf2(x[6], x[7]));
+            *reinterpret_cast<uint4*>(base + kv_feat(kvo, fk + 8)) = make_uint4(pack_bf2(x[8], x[9]), pack_bf2(x[10], x[11]), pack_bf2(x[12], x[13]), pack_bf2(x[14], x[15]));
+          }
         }
       } else if (ep.mode == EPI_RESID) {
         const float4* r4 = reinterpret_cast<const float4*>(ep.resid + (size_t)row * N + f0);

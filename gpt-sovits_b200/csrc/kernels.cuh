@@ -213,8 +213,9 @@ __global__ void __launch_bounds__(64) k_prefill_attn(Ctx c, int layer, const QTi
         const size_t off = (size_t)kv_row_off(pt[p >> PAGE_SHIFT], p & (PAGE - 1)) + (size_t)head * KV_HEAD_STRIDE;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const uint4 kk = *reinterpret_cast<const uint4*>(kbase + off + ch * 8);
-          const uint4 vv = *reinterpret_cast<const uint4*>(vbase + off + ch * 8);
+          const int pc = (ch ^ ((p >> 1) & 3)) * 8;  // chunks of a head row are swizzled by position (common.cuh kv_feat)
+          const uint4 kk = *reinterpret_cast<const uint4*>(kbase + off + pc);
+          const uint4 vv = *reinterpret_cast<const uint4*>(vbase + off + pc);
           float* kd = &Ks[tid][ch * 8];
           float* vd = &Vs[tid][ch * 8];
           kd[0] = bf_lo(kk.x); kd[1] = bf_hi(kk.x); kd[2] = bf_lo(kk.y); kd[3] = bf_hi(kk.y);

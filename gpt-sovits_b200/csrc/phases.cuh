@@ -226,8 +226,8 @@ __device__ void proj_phase(const Ctx& c, const ProjArgs& a, int n_rows, int cta,
               c.q[(size_t)r * D + f] = val * QSCALE;
             } else {
               const size_t off = (size_t)a.layer * c.kv_layer_stride + (size_t)kvoff[n];
-              if (f < 2 * D) c.kpool[off + kv_feat(f - D)] = __float2bfloat16_rn(val);
-              else c.vpool[off + kv_feat(f - 2 * D)] = __float2bfloat16_rn(val);
+              if (f < 2 * D) c.kpool[off + kv_feat(kvoff[n], f - D)] = __float2bfloat16_rn(val);
+              else c.vpool[off + kv_feat(kvoff[n], f - 2 * D)] = __float2bfloat16_rn(val);
             }
           }
         } else if (OUT == OUT_O) {
@@ -396,13 +396,15 @@ template <int U>
 __device__ __forceinline__ void attn_load(const bf16* kbase, const bf16* vbase, const int* pt, int p0, int pend, int lane,
                                           uint4 (&ka)[U], uint4 (&kb)[U], uint4 (&va)[U], uint4 (&vb)[U]) {
   const int page = pt[p0 >> PAGE_SHIFT];
-  // lane l: 16-byte chunk of head l/4 (dims 8*(l%4)..+7) and of head 8 + l/4 (head-major pages, see kv_row_off)
-  const size_t rowoff = (size_t)kv_row_off(page, p0 & (PAGE - 1)) + (size_t)(lane >> 2) * KV_HEAD_STRIDE + (lane & 3) * 8;
+  // lane l: 16-byte chunk of head l/4 (dims 8*(l%4)..+7) and of head 8 + l/4 (head-major pages, chunks swizzled by position)
+  const int pin = p0 & (PAGE - 1);
+  const size_t rowoff = (size_t)kv_row_off(page, pin) + (size_t)(lane >> 2) * KV_HEAD_STRIDE;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (p0 + u < pend) {
-      const bf16* kr = kbase + rowoff + (size_t)u * DH;
-      const bf16* vr = vbase + rowoff + (size_t)u * DH;
+      const int ch = ((lane & 3) ^ (((pin + u) >> 1) & 3)) * 8;
+      const bf16* kr = kbase + rowoff + (size_t)u * DH + ch;
+      const bf16* vr = vbase + rowoff + (size_t)u * DH + ch;
       ka[u] = ld_cg16(kr);
       kb[u] = ld_cg16(kr + 8 * KV_HEAD_STRIDE);
       va[u] = ld_cg16(vr);

@@ -16,7 +16,7 @@ PER = 13  # markers per layer
 nm = 2 + 24 * PER + 6
 slots = (nm + 1) // 2
 ncta = 16 * 7
-tl = torch.zeros((ncta, slots * 2), dtype=torch.int64, device="cuda")
+tl = torch.zeros((ncta + 1, slots * 2), dtype=torch.int64, device="cuda")
 _lib.check(eng.lib.t2s_set_timeline(eng._h, tl.data_ptr(), a.at, slots))
 L = synthetic.config_lens(a.batch, a.lo, a.hi, seed=100)
 ids, lens, prompt, bert = synthetic.make_inputs(a.batch, L, a.prompt, seed=200)
@@ -37,3 +37,4 @@ for cta in (0, 5, 15):
     print("  layer total mean %.2f us, x24 = %.1f us; layer 0: %s" % (lay.sum(axis=1).mean(), lay.sum(), np.round(lay[0], 2)))
     tail = d[1 + 24 * PER:]
     print("  tail (head gemv, cluster barrier, sample, gbar1, plan+gbar2):", np.round(tail, 2))
+
