@@ -751,16 +751,13 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
       CK(cudaMemsetAsync(e->cd.bar, 0, 4, s));
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3(ncl * cs::C); lc.blockDim = dim3(cs::NTC); lc.dynamicSmemBytes = sizeof(cs::Smem); lc.stream = s;
-      cudaLaunchAttribute at[2];
+      // Cluster launch.  Every CTA is co-resident (grid <= cudaOccupancyMaxActiveClusters, one request at a time per engine),
+      // which is what the per-step grid barrier needs; the cooperative attribute is not combined with cluster dimensions
+      // (profilers reject that launch).
+      cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs::C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-      lc.attrs = at; lc.numAttrs = 2;
-      cudaError_t le = cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget);
-      if (le != cudaSuccess) {  // cooperative + cluster rejected: every CTA is co-resident anyway (grid <= max active clusters)
-        cudaGetLastError();
-        lc.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget));
-      }
+      lc.attrs = at; lc.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget));
       e->launches++;
     } else if (mode == 1) {
       int grid = e->cd.attn_ctas;

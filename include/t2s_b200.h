@@ -140,16 +140,21 @@ int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, int32_t widt
                      int32_t step, int32_t* tok_out, int32_t* greedy_out, void* stream);
 
 /* Measurement hook: during persistent-kernel iteration `step` of the next t2s_decode, thread 0 of every CTA
- * records its SM clock when it arrives at / is released from each grid barrier:
- * buf[cta][slots][2] (device, int64).  Set before t2s_prefill; NULL clears. */
+ * records its SM clock when it arrives at / is released from each grid barrier (mode 1: buf[cta][slots][2]) or at
+ * the phase markers of the cluster-stream kernel (mode 4: buf[cta][2*slots] consecutive stamps), device int64.
+ * Set before t2s_prefill; NULL clears. */
 int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int32_t slots);
 
 /* Measurement hook: latency of n_barriers back-to-back grid barriers of the persistent kernel. */
 int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* ms_out, void* stream);
 
 enum {
-  T2S_OPT_DECODE_MODE = 0,   /* 0: one kernel per phase, CUDA-graph replay; 1: persistent cooperative kernel;
-                                2: one kernel per phase, plain stream launches (profiling aid);
+  T2S_OPT_DECODE_MODE = 0,   /* 5 (default): auto = 4 when the batch fits the cluster-stream kernel (<= 8 sequences per
+                                co-resident 16-CTA cluster: 56 on a B200), else 1;
+                                4: cluster-stream kernel: thread-block clusters own sequences end to end, no grid barrier
+                                   inside a step (all remaining steps of the request in ONE launch);
+                                0: one kernel per phase over all SMs, CUDA-graph replay; 1: the same phases in one
+                                persistent cooperative kernel with grid barriers; 2: plain stream launches (profiling aid);
                                 3: CUDA graph with the projections on tcgen05 tensor cores (large batches);
                                 mode 1 switches to 3 by itself when batch >= T2S_OPT_TC_DECODE_MIN_BATCH */
   T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */

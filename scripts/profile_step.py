@@ -9,7 +9,7 @@ import ctypes as C
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=100)
-ap.add_argument("--mode", type=int, default=1)
+ap.add_argument("--mode", type=int, default=5)
 ap.add_argument("--prompt", type=int, default=150)
 ap.add_argument("--lo", type=int, default=60)
 ap.add_argument("--hi", type=int, default=120)

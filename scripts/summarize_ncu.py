@@ -31,7 +31,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
         "launch__shared_mem_per_block_dynamic"]
 import json
-for rep, title in (("prof_decode_b32", "k_decode_persistent: the bench workload's decode launch (B=32, 1000 steps in ONE launch, mean KV 743) — `ncu --set full --clock-control none`"),
+for rep, title in (("prof_decode_b32", "k_decode_cluster: the bench workload's decode launch (B=32, 1000 steps in ONE launch of 7 clusters x 16 CTAs, mean KV 743) — `ncu --set full --clock-control none`"),
                    ("prof_gemm_b32", "k_gemm_tc<128> (tcgen05/TMEM + TMA prefill projections), B=32 (7755 rows) — `ncu --set full`"),
                    ("prof_pattn_b32", "k_prefill_attn (prefix-LM attention), B=32 — `ncu --set full`")):
     path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
@@ -53,7 +53,7 @@ for rep, title in (("prof_decode_b32", "k_decode_persistent: the bench workload'
             def val(nm):
                 i = hdr.index(nm); x = float(r[i].replace(",", "")); u = units[i].lower()
                 return x * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1, "tbyte": 1e12}.get(u, 1)
-            tr = {"kernel": name, "workload": "cfg2_b32", "decode_steps": 1000,
+            tr = {"kernel": name, "workload": "cfg2_b32", "decode_steps": 1000, "decode_mode": 4 if "cluster" in name else 1,
                   "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                   "note": "one ncu --set full capture of the whole 1000-step persistent launch (profiler-time duration is not a bench number)"}
             json.dump(tr, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
