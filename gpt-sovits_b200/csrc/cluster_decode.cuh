@@ -116,6 +116,24 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
                "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
 }
+// L2 eviction policies: the K/V cache is read once per step (evict first), the weight streams are re-read by every cluster
+// (evict last), so the 1.2 GB of K/V that flow through L2 every step do not push the 152 MB of weights out
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint4 ld_weight16_keep(const void* p, uint64_t policy) {  // read-only path, no L1, L2 evict-last
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint32_t bytes, void* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(s32(dst)),
+               "l"(src), "r"(bytes), "r"(s32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_idx() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t n_clusters() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -237,8 +255,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 constexpr int FB = 16;
 template <int N>
 __device__ __forceinline__ void ldg_batch(const uint4* p, uint4 (&f)[FB]) {  // p = warp's fragment base + lane
+  const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
-  for (int i = 0; i < N; ++i) f[i] = ld_weight16(p + i * 32);
+  for (int i = 0; i < N; ++i) f[i] = ld_weight16_keep(p + i * 32, keep);
 }
 // One matrix slice of this warp = NF fragments (k-blocks kb0 .. kb0+NF-1 of one 16-feature tile); buf = its first
 // min(NF, FB) fragments (already in flight / landed).  acc = 16 features x 8 sequences in the m16n8k16 C layout (c0,c1:
@@ -255,11 +274,12 @@ __device__ __forceinline__ void gemv_ldg(const uint4* wp, uint4 (&buf)[FB], cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
   const bf16* arow = act + g * ROWS + (kb0 / SKB) * SRCS;  // kb0 is a multiple of SKB
+  const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
   for (int k = 0; k < NF; ++k) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(arow + (k / SKB) * SRCS + (k % SKB) * 16);
     mma_bf16_16816(a[k & 3], buf[k % FB], xr[t], xr[4 + t]);
-    if (k + FB < NF) buf[k % FB] = ld_weight16(wp + (k + FB) * 32);
+    if (k + FB < NF) buf[k % FB] = ld_weight16_keep(wp + (k + FB) * 32, keep);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = (a[0][j] + a[1][j]) + (a[2][j] + a[3][j]);
@@ -366,13 +386,21 @@ struct KvStream { unsigned base; int total, ptot; };  // ring index of the step'
 __device__ __forceinline__ void kv_issue(const Ctx& c, Smem& sm, unsigned idx, int layer, int rem, uint32_t rank) {
   const int e = sm.pmap[rem], n = e >> 8, pg = e & 0xFF;
   const int pos = sm.row_pos[n];
-  const uint32_t bytes = (uint32_t)(PAGE * DH * 2 + min(PAGE, pos - pg * PAGE) * DH * 2);  // K block + the valid V rows
+  const int np = min(PAGE, pos - pg * PAGE);  // valid positions of the page
   const bf16* src = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE + (size_t)sm.pt[n][pg] * KV_PAGE_STRIDE;
   const unsigned slot = ring_slot(idx);
+  const uint64_t pol = l2_policy_evict_first();
   // (the slot's previous page was read by this warp's ldmatrix, complete before the MMAs that consumed it were issued;
   //  the generic -> async proxy fence for K/V rows appended in earlier steps is executed once per step by the caller)
-  mbar_expect_tx(&sm.full[slot], bytes);
-  bulk_load(sm.ring[slot], src, bytes, &sm.full[slot]);
+  if (np == PAGE) {  // a full page: K block and V block are one contiguous 16 KB
+    mbar_expect_tx(&sm.full[slot], 2 * PAGE * DH * 2);
+    bulk_load_hint(sm.ring[slot], src, 2 * PAGE * DH * 2, &sm.full[slot], pol);
+  } else {           // the last page of a sequence: only its valid K rows and V rows (no over-fetch)
+    const uint32_t bytes = (uint32_t)np * DH * 2;
+    mbar_expect_tx(&sm.full[slot], 2 * bytes);
+    bulk_load_hint(sm.ring[slot], src, bytes, &sm.full[slot], pol);
+    bulk_load_hint(sm.ring[slot] + PAGE * DH * 2, src + KV_V_OFF, bytes, &sm.full[slot], pol);
+  }
 }
 
 __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvStream& ks, uint32_t rank, int layer, unsigned& cons,
