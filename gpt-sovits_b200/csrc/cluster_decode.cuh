@@ -83,7 +83,7 @@ struct __align__(128) Smem {
   alignas(16) float vec[2][VC_FLOATS];  // the layer's vectors (biases of the own slices, LayerNorm gamma / beta): 2-deep ring of its own
   int row_npg[RMAX];                  // cached pages per sequence this step
   unsigned short pmap[RMAX * 32];     // page q of a layer (consumption order) -> (sequence << 8) | page
-  unsigned long long full[NSLOT], vfull[2], ebar[4], cbar;
+  unsigned long long kfull[NSLOT], vfull_kv[NSLOT], vfull[2], ebar[4], cbar;  // K half / V half of a ring slot land separately
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------------
@@ -383,24 +383,26 @@ __device__ __forceinline__ uint32_t pack_bf2_exact(float a, float b) { return __
 struct KvStream { unsigned base; int total, ptot; };  // ring index of the step's first page; pages per step; pages per layer
 // lane 0 of the owning warp: start the TMA copy of ring index idx (= page `rem` of layer `layer`, rem < ptot) into its slot.
 // sm.pmap[rem] = (sequence << 8) | page was filled by the step prologue.
-__device__ __forceinline__ void kv_issue(const Ctx& c, Smem& sm, unsigned idx, int layer, int rem, uint32_t rank) {
+__device__ __forceinline__ void kv_issue(const Ctx& c, Smem& sm, unsigned idx, int layer, int rem, uint32_t rank, bool v_half) {
   const int e = sm.pmap[rem], n = e >> 8, pg = e & 0xFF;
   const int pos = sm.row_pos[n];
-  const int np = min(PAGE, pos - pg * PAGE);  // valid positions of the page
-  const bf16* src = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE + (size_t)sm.pt[n][pg] * KV_PAGE_STRIDE;
+  const uint32_t bytes = (uint32_t)min(PAGE, pos - pg * PAGE) * DH * 2;  // only the valid rows (the last page is partial)
+  const bf16* src = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE + (size_t)sm.pt[n][pg] * KV_PAGE_STRIDE +
+                    (v_half ? KV_V_OFF : 0);
   const unsigned slot = ring_slot(idx);
-  const uint64_t pol = l2_policy_evict_first();
-  // (the slot's previous page was read by this warp's ldmatrix, complete before the MMAs that consumed it were issued;
-  //  the generic -> async proxy fence for K/V rows appended in earlier steps is executed once per step by the caller)
-  if (np == PAGE) {  // a full page: K block and V block are one contiguous 16 KB
-    mbar_expect_tx(&sm.full[slot], 2 * PAGE * DH * 2);
-    bulk_load_hint(sm.ring[slot], src, 2 * PAGE * DH * 2, &sm.full[slot], pol);
-  } else {           // the last page of a sequence: only its valid K rows and V rows (no over-fetch)
-    const uint32_t bytes = (uint32_t)np * DH * 2;
-    mbar_expect_tx(&sm.full[slot], 2 * bytes);
-    bulk_load_hint(sm.ring[slot], src, bytes, &sm.full[slot], pol);
-    bulk_load_hint(sm.ring[slot] + PAGE * DH * 2, src + KV_V_OFF, bytes, &sm.full[slot], pol);
-  }
+  void* bar = v_half ? (void*)&sm.vfull_kv[slot] : (void*)&sm.kfull[slot];
+  // The K half and the V half of a slot are copied separately: the next page's K is requested as soon as this page's scores
+  // are out, its V after the PV product, so each copy overlaps the other half's compute.  (The half's previous contents were
+  // read by this warp's ldmatrix, complete before the MMAs that consumed them; the generic -> async proxy fence for rows
+  // appended in earlier steps is executed once per step by the caller.)
+  mbar_expect_tx(bar, bytes);
+  bulk_load_hint(sm.ring[slot] + (v_half ? PAGE * DH * 2 : 0), src, bytes, bar, l2_policy_evict_first());
+}
+// ring index idx + 8 -> (layer, page-in-layer) of the next page of this warp's slot; false past the end of the step
+__device__ __forceinline__ bool kv_next(const Ctx& c, const KvStream& ks, int layer, int page_in_layer, int& nl, int& nr) {
+  nl = layer; nr = page_in_layer + NSLOT;
+  while (nr >= ks.ptot) { nr -= ks.ptot; ++nl; }
+  return nl < c.n_layer;
 }
 
 __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvStream& ks, uint32_t rank, int layer, unsigned& cons,
@@ -440,7 +442,9 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
         const int np = min(PAGE, pos - pg * PAGE);
         const int ntile = (np + 15) >> 4;
         const unsigned slot = ring_slot(j + pg);
-        mbar_wait(&sm.full[slot], ring_par(j + pg));
+        mbar_wait(&sm.kfull[slot], ring_par(j + pg));
+        int nl, nr;
+        const bool more = kv_next(c, ks, layer, (int)(j + pg - cons), nl, nr);
         const uint32_t base = s32(sm.ring[slot]);
         float sc[8][2];
         float mx = -INFINITY;
@@ -471,6 +475,7 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
             mx = fmaxf(mx, fmaxf(sc[pt][0], sc[pt][1]));
           }
         }
+        if (lane == 0 && more) kv_issue(c, sm, j + pg + NSLOT, nl, nr, rank, false);  // K half is free: next page's K
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
@@ -489,6 +494,7 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[mt][i] *= corr;
+        mbar_wait(&sm.vfull_kv[slot], ring_par(j + pg));
         {
           // B fragments of P: positions 16kb + (2t, 2t+1 | 2t+8, 2t+9) are held by the quads g' = 2t and 2t+1
           uint32_t pb[8][2];
@@ -525,11 +531,7 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
             for (int i = 0; i < 4; ++i) o[mt][i] += o2[mt][i];
         }
         __syncwarp();
-        if (lane == 0) {  // the slot is free again: fetch the next page that maps to it (8 pages on, possibly in a later layer)
-          int nl = layer, nr = (int)(j + pg - cons) + NSLOT;  // page number inside the layer
-          while (nr >= ks.ptot) { nr -= ks.ptot; ++nl; }
-          if (nl < c.n_layer) kv_issue(c, sm, j + pg + NSLOT, nl, nr, rank);
-        }
+        if (lane == 0 && more) kv_issue(c, sm, j + pg + NSLOT, nl, nr, rank, true);  // V half is free: next page's V
       }
       // the quads hold disjoint positions: sum l over g (every column of O already covers all positions of the pages)
       l += __shfl_xor_sync(0xffffffffu, l, 4);
@@ -607,7 +609,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), cid = cluster_idx(), ncl = n_clusters();
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.kfull[s], 1); mbar_init(&sm.vfull_kv[s], 1); }
     for (int k = 0; k < 4; ++k) mbar_init(&sm.ebar[k], 1);
     for (int k = 0; k < 2; ++k) mbar_init(&sm.vfull[k], 1);
     mbar_init(&sm.cbar, C);
@@ -706,7 +708,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
           int nl = 0, nr = (warp - cons) & (NSLOT - 1);  // the first page of the step that maps to this warp's slot
           const unsigned first = cons + nr;
           while (nr >= ks.ptot) { nr -= ks.ptot; ++nl; }
-          if (nl < c.n_layer) kv_issue(c, sm, first, nl, nr, rank);
+          if (nl < c.n_layer) { kv_issue(c, sm, first, nl, nr, rank, false); kv_issue(c, sm, first, nl, nr, rank, true); }
         }
         CS_TL();
         for (int layer = 0; layer < c.n_layer; ++layer) {
