@@ -624,6 +624,9 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
   // weight stream -> L2: unit u = layer (u % units_per_step) or the head; every warp pulls its eighth of unit u, two units
   // ahead of the compute.  The units of the next step are the same bytes, so running ahead is always legal.
   auto prefetch_unit = [&](int u) {
+#ifdef CS_NO_WPF
+    return;
+#endif
     if (lane != 0) return;
     const int layer = u % units_per_step;
     if (layer < c.n_layer) l2_prefetch(wstream + ((size_t)layer * C + rank) * LAYER_BYTES + (size_t)warp * (LAYER_BYTES / NCW), LAYER_BYTES / NCW);

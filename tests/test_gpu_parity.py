@@ -422,6 +422,41 @@ def test_large_batch_tcgen05_decode(engine):
     assert int(res_tc.stats["decode_steps"]) == int(res_pk.stats["decode_steps"]) == max(res_tc.idx)
 
 
+@pytest.mark.parametrize("B,P,lo,hi", [(20, 30, 16, 48), (56, 140, 100, 260)])
+def test_cluster_stream_multi_row_vs_phase_kernels(engine, B, P, lo, hi):
+    """The cluster-stream kernel with several sequences per cluster (3 and 8 rows per 16-CTA cluster; the second case also
+    crosses 128-position K/V page boundaries: up to 3 pages per sequence, partial last pages) against the grid-wide phase
+    kernels on the same teacher-forced run with EOS forced at different steps: logits within the tolerance, identical
+    retirement (idx) and tokens."""
+    from gpt_sovits_b200 import _lib
+    n = 12
+    L = synthetic.config_lens(B, lo, hi, seed=19)
+    ids, lens, prompt, bert = synthetic.make_inputs(B, L, P, seed=37)
+    ids = [t.cuda() for t in ids]
+    bert = [t.cuda() for t in bert]
+    prompt = prompt.cuda()
+    g = torch.Generator().manual_seed(5)
+    forced = torch.randint(0, 1024, (B, n), dtype=torch.int32, generator=g)
+    stop = torch.randint(3, n, (B,), generator=g)
+    for b in range(0, B, 3):
+        forced[b, int(stop[b])] = 1024  # every third utterance retires early: rows are re-dealt to the clusters
+    kw = dict(top_k=1, early_stop_num=n - 1, eos_suppress_steps=1, forced=forced, capture_logits=n)
+    engine.set_option(_lib.OPT_DECODE_MODE, 5)
+    res_cs = engine.infer(ids, bert, prompt, **kw)
+    assert int(res_cs.stats["decode_mode"]) == 4
+    engine.set_option(_lib.OPT_DECODE_MODE, 1)
+    res_pk = engine.infer(ids, bert, prompt, **kw)
+    assert int(res_pk.stats["decode_mode"]) == 1
+    assert res_cs.idx == res_pk.idx
+    assert len(set(res_cs.idx)) > 3
+    a, b_ = res_cs.logits.cpu().numpy(), res_pk.logits.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b_))
+    d = float(np.nanmax(np.abs(a[:, :, :1024] - b_[:, :, :1024])))
+    print(f"cluster-stream (B={B}) vs phase kernels: max |dlogit| = {d:.4f}")
+    assert d <= LOGIT_TOL
+    assert torch.equal(res_cs.tokens, res_pk.tokens)
+
+
 def test_drop_in_patch_with_fake_tts_caller(weights_seed0, pe_table):
     """The class-level patch, driven the way TTS.run drives the reference (TTS.py:1042-1047, 1210-1227,
     1259): instance-level rebinding to the batched variant, prompt as an .expand view, fp16 BERT
