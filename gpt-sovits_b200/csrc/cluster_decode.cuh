@@ -659,30 +659,41 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
     // this warp's fragment streams inside a layer block (uint4 units), + lane
     const size_t wq = (OFFS_QKV + (size_t)warp * NF_QKV * 512) / 16 + lane, wo = (OFFS_WO + (size_t)warp * NF_WO * 512) / 16 + lane,
                  w1 = (OFFS_W1 + (size_t)warp * NF_W1 * 512) / 16 + lane, w2 = (OFFS_W2 + (size_t)warp * NF_W2 * 512) / 16 + lane;
-    for (int it = 0; it < max_new_steps; ++it) {
-      const int n_act = ld_cg_i(c.n_active);
+    // Retirement bookkeeping (phase_plan by CTA 0 + a second grid barrier) only runs in steps in which a sequence stopped
+    // (stop flag in c.seg_cnt[step % 3], set by the sampling CTA); otherwise every sequence just advances by one position
+    // and each CTA updates its own copy of the row descriptors.
+    int step = ld_cg_i(c.step);
+    int n_act = 0, R = 0;
+    bool fresh = true;  // row descriptors have to be (re)read from global memory: first step, or after a plan
+    for (int it = 0; it < max_new_steps; ++it, ++step) {
+      if (fresh) {
+        n_act = ld_cg_i(c.n_active);
+        R = ((int)cid < n_act) ? (n_act - (int)cid + (int)ncl - 1) / (int)ncl : 0;  // rows r = n*ncl + cid
+      }
       if (n_act == 0 || __ldcg(c.abort_flag) != 0) break;
       tl = (c.timeline && it == c.tl_step) ? c.timeline + (size_t)blockIdx.x * c.tl_slots * 2 : nullptr;
       tk = 0;
       CS_TL();
-      const int R = ((int)cid < n_act) ? (n_act - (int)cid + (int)ncl - 1) / (int)ncl : 0;  // rows r = n*ncl + cid
+      bool stopped = false;
       if (R > 0) {
         uint4 wf[FB];  // first fragment batch of the next matrix, in flight across the hand-off that precedes it
         const uint4* lw = reinterpret_cast<const uint4*>(wstream + (size_t)rank * LAYER_BYTES);
         if (warp < NW_QKV) ldg_batch<FB>(lw + wq, wf);
         // ---- step prologue: row descriptors, page-table rows, layer-0 input
-        if (tid < R) {
-          const int r = tid * ncl + cid;
-          sm.row_slot[tid] = ld_cg_i(c.row_slot + r);
-          sm.row_pos[tid] = ld_cg_i(c.row_pos + r);
-          sm.row_kvoff[tid] = __ldcg(c.row_kvoff + r);
-          sm.row_npg[tid] = (sm.row_pos[tid] + PAGE - 1) >> PAGE_SHIFT;
+        if (fresh) {
+          if (tid < R) {
+            const int r = tid * ncl + cid;
+            sm.row_slot[tid] = ld_cg_i(c.row_slot + r);
+            sm.row_pos[tid] = ld_cg_i(c.row_pos + r);
+            sm.row_kvoff[tid] = __ldcg(c.row_kvoff + r);
+          }
+          csync();
+          for (int i = tid; i < R * 32; i += NCW * 32) {
+            const int n = i >> 5, pg = i & 31;
+            sm.pt[n][pg] = (pg < c.max_pages) ? c.page_table[sm.row_slot[n] * c.max_pages + pg] : 0;  // whole row: later steps advance locally
+          }
         }
-        csync();
-        for (int i = tid; i < R * 32; i += NCW * 32) {
-          const int n = i >> 5, pg = i & 31;
-          sm.pt[n][pg] = (pg <= (sm.row_pos[n] >> PAGE_SHIFT)) ? c.page_table[sm.row_slot[n] * c.max_pages + pg] : 0;
-        }
+        if (tid < R) sm.row_npg[tid] = (sm.row_pos[tid] + PAGE - 1) >> PAGE_SHIFT;
         if (warp < R) {
           const int n = warp;
           const float* xr = c.x0 + (size_t)sm.row_slot[n] * D;
@@ -846,13 +857,40 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
         mbar_wait_cluster(&sm.cbar, cpar); cpar ^= 1u;
         CS_TL();
         // ---- sampler: CTA `rank` takes the cluster's sequence `rank`
-        if ((int)rank < R) sample_row<1>(c, (int)rank * ncl + cid, ld_cg_i(c.step), ss);
+        if ((int)rank < R) {
+          stopped = sample_row<1>(c, (int)rank * ncl + cid, step, ss);
+          if (stopped && tid == 0) c.seg_cnt[step % 3] = 1;
+        }
       }
       CS_TL();
       gbar.sync();
       CS_TL();
-      if (blockIdx.x == 0) phase_plan<1>(c, reinterpret_cast<int*>(sm.e13));
-      gbar.sync();
+      if (ld_cg_i(c.seg_cnt + step % 3) != 0) {
+        // somebody stopped: compact the active list, re-deal the rows (t2s_model.py:724-745 does this on the host)
+        if (blockIdx.x == 0) phase_plan<1>(c, reinterpret_cast<int*>(sm.e13));
+        gbar.sync();
+        if (blockIdx.x == 0 && tid == 0) c.seg_cnt[step % 3] = 0;  // every CTA read it before the barrier; next use in 3 steps
+        fresh = true;
+      } else {
+        // nobody stopped: every sequence moves on by one position (what phase_plan would have computed)
+        if ((int)rank < R && tid == 0) {
+          const int slot = sm.row_slot[rank], pos = sm.row_pos[rank] + 1;
+          c.seq_len[slot] = pos + 1;
+          atomicAdd(c.stats + 0, (unsigned long long)(pos + 1));
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+          *c.step = step + 1;
+          atomicAdd(c.stats + 1, 1ull);
+          atomicAdd(c.stats + 2, (unsigned long long)n_act);
+        }
+        if (tid < R) {
+          const int pos = sm.row_pos[tid] + 1;
+          sm.row_pos[tid] = pos;
+          sm.row_kvoff[tid] = kv_row_off(sm.pt[tid][pos >> PAGE_SHIFT], pos & (PAGE - 1));
+        }
+        csync();
+        fresh = false;
+      }
       CS_TL();
     }
 #undef CS_TL

@@ -661,9 +661,18 @@ __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV],
     cta_sync<SB>();
     sm.hist[tid] = 0;  // NT == 256 bins
     cta_sync<SB>();
+    // warp-aggregated histogram: logits crowd into a few bins of the leading byte, and same-address shared-memory atomics
+    // serialise; lanes with the same bin elect a leader that adds their count once
 #pragma unroll
-    for (int j = 0; j < SV; ++j)
-      if (valid[j] && (key[j] & mask) == prefix) atomicAdd(&sm.hist[(key[j] >> shift) & 0xFFu], 1u);
+    for (int j = 0; j < SV; ++j) {
+      const bool act = valid[j] && (key[j] & mask) == prefix;
+      const unsigned bin = (key[j] >> shift) & 0xFFu;
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const unsigned peers = __match_any_sync(am, bin);
+        if (lane == __ffs(peers) - 1) atomicAdd(&sm.hist[bin], (unsigned)__popc(peers));
+      }
+    }
     cta_sync<SB>();
     if (warp == 0) {
       // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches k
@@ -770,7 +779,7 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
 }
 
 template <int SB>
-__device__ void sample_row(const Ctx& c, int r, int step, SampSmem& sm) {
+__device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm) {  // returns: the sequence stopped at this step
   const int tid = threadIdx.x;
   const int width = (step < c.eos_window) ? (V - 1) : V;
   {
@@ -869,6 +878,7 @@ __device__ void sample_row(const Ctx& c, int r, int step, SampSmem& sm) {
       }
     }
     cta_sync<SB>();
+    return stop;
   }
 }
 
