@@ -25,6 +25,38 @@ __global__ void k_mma(int n, int chains, float* out, long long* cyc) {
 __device__ __forceinline__ uint4 ldw(const void* p) {
   uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
 }
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ldw256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+  return r;
+}
+// 256-bit loads: 8 in flight per lane (same bytes in flight as 16 x 128-bit)
+__global__ void k_ldg256(const unsigned char* base, int per_warp, int reps, unsigned* sink, long long* cyc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const unsigned char* p0 = base + ((size_t)blockIdx.x * nw + warp) * per_warp + lane * 32;
+  unsigned acc = 0;
+  const int nb = per_warp / 8192;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    U8 f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = ldw256(p0 + j * 1024);
+    for (int b = 1; b <= nb; ++b) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc ^= f[j].v[0] ^ f[j].v[7];
+        if (b < nb) f[j] = ldw256(p0 + (size_t)(b * 8 + j) * 1024);
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (acc == 0x1234567u) sink[0] = acc;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
 // each warp streams its own contiguous slice of `per_warp` bytes, `reps` times (L2 resident after the first pass)
 __global__ void k_ldg(const unsigned char* base, int per_warp, int reps, unsigned* sink, long long* cyc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -72,5 +104,15 @@ int main() {
       printf("ld.global.nc 128-bit, L2 resident: %3d CTAs x %2d warps, 16 in flight per lane: %.1f B/clk/SM (%.0f GB/s per SM @1.9GHz)\n", ctas, warps,
              (double)warps * per_warp * reps / c, (double)warps * per_warp * reps / c * 1.9);
     }
+  for (int ctas : {1, 16, 112})
+    for (int warps : {8}) {
+      const int per_warp = 49152, reps = 50;
+      k_ldg256<<<ctas, warps * 32>>>(buf, per_warp, reps, sink, cyc); CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h, cyc, ctas * 8, cudaMemcpyDeviceToHost));
+      double c = 0; for (int i = 0; i < ctas; ++i) c += h[i]; c /= ctas;
+      printf("ld.global.nc 256-bit, L2 resident: %3d CTAs x %2d warps, 8 in flight per lane: %.1f B/clk/SM (%.0f GB/s per SM @1.9GHz)\n", ctas, warps,
+             (double)warps * per_warp * reps / c, (double)warps * per_warp * reps / c * 1.9);
+    }
+  // same data for every CTA (what the 7 clusters do with the weight stream): 112 CTAs, all reading CTA 0's slices
   return 0;
 }
