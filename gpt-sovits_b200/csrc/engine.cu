@@ -747,8 +747,8 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
     }
     e->st.decode_mode = mode;
     if (mode == 4) {
-      const int ncl = std::min(e->max_clusters, e->B);
-      CK(cudaMemsetAsync(e->cd.bar, 0, 4, s));
+      const int ncl = e->max_clusters;  // always the full set: clusters without a sequence pull the weight stream into L2 for the others
+      CK(cudaMemsetAsync(e->cd.bar, 0, 8, s));  // grid-barrier counter + the progress word of the prefetching clusters
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3(ncl * cs::C); lc.blockDim = dim3(cs::NTC); lc.dynamicSmemBytes = sizeof(cs::Smem); lc.stream = s;
       // Cluster launch.  Every CTA is co-resident (grid <= cudaOccupancyMaxActiveClusters, one request at a time per engine),
