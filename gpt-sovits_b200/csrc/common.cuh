@@ -110,6 +110,7 @@ struct Ctx {
   int attn_ctas;    // grid size of the decode attention phase (fixed for the session)
   // session (indexed by slot = original batch index)
   int B0, P, max_steps, eos_window, early_stop, top_k;
+  int slot_base;  // first utterance of this session inside the caller's batch (t2s_generate splits large batches): keeps the Philox streams per utterance
   float top_p, temperature, rep_pen;
   uint32_t seed_lo, seed_hi;
   int* step;

@@ -97,6 +97,7 @@ struct t2s_engine {
   int tl_step = 0, tl_slots = 0;
   int decode_mode = 5, prefill_gemm = 0, num_ctas = 0, check_steps = 16, tc_decode_min_batch = 160;
   int graph_mode = -1;
+  int slot_base = 0;  // set by t2s_generate while it runs a large batch in chunks
   bool tc_ok = false;
   DevBuf xf, xb;  // tcgen05 prefill path: LayerNorm'ed rows (fp32 residual + bf16 GEMM operand)
   // graph cache (decode_mode 0)
@@ -626,6 +627,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
   c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
   c.seed_lo = (uint32_t)(rq->seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(rq->seed >> 32);
+  c.slot_base = e->slot_base;
   c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
   c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
   c.seen = e->seen.as<uint32_t>();
@@ -859,10 +861,49 @@ extern "C" int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride
 
 extern "C" int t2s_generate(t2s_engine* e, const t2s_request* rq, int64_t* tokens_out, int64_t row_stride,
                             int32_t tokens_on_host, int32_t* idx_out, void* stream) {
-  if (t2s_prefill(e, rq, stream)) return 1;
-  int32_t n = 0;
-  if (t2s_decode(e, -1, stream, &n)) return 1;
-  return t2s_result(e, tokens_out, row_stride, tokens_on_host, idx_out, stream);
+  if (!e || !rq) return fail("t2s_generate: null argument");
+  // Auto mode: a batch that does not fit the cluster-stream kernel (8 sequences per co-resident cluster) is run as equal
+  // chunks that do, one after the other (sequences never interact: t2s_model.py:583-779 has no cross-sequence op).  Measured:
+  // 2 x 32 sequences take 2 x 450 us per step against 1100 us for 64 on the grid-wide phase kernels.  From
+  // T2S_OPT_TC_DECODE_MIN_BATCH on the tcgen05 projections of mode 3 are the faster path and the batch stays whole.
+  const int fit = e->max_clusters * cs::RMAX;
+  const bool hooks = e->forced || e->logits_rec || e->timeline;
+  const bool whole = e->decode_mode != 5 || fit < 1 || rq->batch <= fit || hooks ||
+                     (e->tc_ok && e->tc_decode_min_batch > 0 && rq->batch >= e->tc_decode_min_batch);
+  if (whole) {
+    if (t2s_prefill(e, rq, stream)) return 1;
+    int32_t n = 0;
+    if (t2s_decode(e, -1, stream, &n)) return 1;
+    return t2s_result(e, tokens_out, row_stride, tokens_on_host, idx_out, stream);
+  }
+  if (rq->batch > e->cfg.max_batch) return fail("t2s_generate: batch %d outside [1,%d]", rq->batch, e->cfg.max_batch);
+  const int B = rq->batch, nchunk = (B + fit - 1) / fit, per = (B + nchunk - 1) / nchunk;
+  t2s_stats acc = e->st;
+  acc.prefill_ms = 0; acc.decode_ms = 0; acc.decode_steps = 0; acc.decode_tokens = 0; acc.decode_kv_positions = 0; acc.prefill_rows = 0;
+  int rc = 0;
+  int64_t id_off = 0;
+  for (int b0 = 0; b0 < B && !rc; b0 += per) {
+    const int n = std::min(per, B - b0);
+    t2s_request sub = *rq;
+    sub.batch = n;
+    sub.phoneme_ids = rq->phoneme_ids + id_off;
+    sub.phoneme_lens = rq->phoneme_lens + b0;
+    sub.bert = rq->bert + b0;
+    sub.bert_stride_c = rq->bert_stride_c + b0;
+    sub.bert_stride_t = rq->bert_stride_t + b0;
+    sub.prompt = rq->prompt ? rq->prompt + (int64_t)b0 * rq->prompt_row_stride : nullptr;
+    for (int b = 0; b < n; ++b) id_off += rq->phoneme_lens[b0 + b];
+    e->slot_base = b0;
+    int32_t steps = 0;
+    rc = t2s_prefill(e, &sub, stream) || t2s_decode(e, -1, stream, &steps) ||
+         t2s_result(e, tokens_out + (int64_t)b0 * row_stride, row_stride, tokens_on_host, idx_out + b0, stream);
+    acc.prefill_ms += e->st.prefill_ms; acc.decode_ms += e->st.decode_ms; acc.decode_steps += e->st.decode_steps;
+    acc.decode_tokens += e->st.decode_tokens; acc.decode_kv_positions += e->st.decode_kv_positions; acc.prefill_rows += e->st.prefill_rows;
+    acc.decode_mode = e->st.decode_mode;
+  }
+  e->slot_base = 0;
+  if (!rc) e->st = acc;
+  return rc;
 }
 
 extern "C" int t2s_get_sampled(t2s_engine* e, int32_t* out, int32_t n_steps, void* stream_) {

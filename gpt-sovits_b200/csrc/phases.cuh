@@ -843,7 +843,7 @@ __device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm) {  // re
         const int i = tid + NT * j;
         if (!valid[j]) continue;
         uint32_t w[4];
-        philox4x32_10((uint32_t)(i >> 2), (uint32_t)step, (uint32_t)slot, 0u, c.seed_lo, c.seed_hi, w);
+        philox4x32_10((uint32_t)(i >> 2), (uint32_t)step, (uint32_t)(slot + c.slot_base), 0u, c.seed_lo, c.seed_hi, w);
         const uint32_t word = w[i & 3];
         const float u = ((float)(word >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
         const float q = -logf(u);

@@ -457,6 +457,33 @@ def test_cluster_stream_multi_row_vs_phase_kernels(engine, B, P, lo, hi):
     assert torch.equal(res_cs.tokens, res_pk.tokens)
 
 
+def test_large_batch_runs_as_cluster_stream_chunks(engine):
+    """Auto mode: a batch that does not fit the cluster-stream kernel (56 sequences) and is below the tcgen05 crossover is
+    run by t2s_generate as equal chunks that do fit.  Greedy decoding is deterministic, so the chunked call must give exactly
+    what the two halves give when they are submitted on their own."""
+    B, P, n = 72, 30, 8
+    L = synthetic.config_lens(B, 16, 48, seed=23)
+    ids, lens, prompt, bert = synthetic.make_inputs(B, L, P, seed=41)
+    ids = [t.cuda() for t in ids]
+    bert = [t.cuda() for t in bert]
+    prompt = prompt.cuda()
+    kw = dict(top_k=1, early_stop_num=n, eos_suppress_steps=1)
+    res = engine.infer(ids, bert, prompt, **kw)
+    assert int(res.stats["decode_mode"]) == 4
+    assert int(res.stats["decode_steps"]) == 2 * n  # two chunks, n decode steps each (prefill samples step 0)
+    h = B // 2
+    ra = engine.infer(ids[:h], bert[:h], prompt[:h], **kw)
+    rb = engine.infer(ids[h:], bert[h:], prompt[h:], **kw)
+    assert res.idx == ra.idx + rb.idx
+    assert torch.equal(res.tokens[:h], ra.tokens) and torch.equal(res.tokens[h:], rb.tokens)
+    # sampling: every utterance keeps its own Philox stream (keyed by its index in the caller's batch), chunked or not
+    kw = dict(top_k=15, temperature=1.0, early_stop_num=n, eos_suppress_steps=1, seed=77)
+    r1 = engine.infer(ids, bert, prompt, **kw)
+    r2 = engine.infer(ids, bert, prompt, **kw)
+    assert r1.idx == r2.idx and torch.equal(r1.tokens, r2.tokens)
+    assert len({tuple(r1.tokens[b, P:P + n].tolist()) for b in range(B)}) > B // 2
+
+
 def test_drop_in_patch_with_fake_tts_caller(weights_seed0, pe_table):
     """The class-level patch, driven the way TTS.run drives the reference (TTS.py:1042-1047, 1210-1227,
     1259): instance-level rebinding to the batched variant, prompt as an .expand view, fp16 BERT
