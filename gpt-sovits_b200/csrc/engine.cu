@@ -864,12 +864,11 @@ extern "C" int t2s_generate(t2s_engine* e, const t2s_request* rq, int64_t* token
   if (!e || !rq) return fail("t2s_generate: null argument");
   // Auto mode: a batch that does not fit the cluster-stream kernel (8 sequences per co-resident cluster) is run as equal
   // chunks that do, one after the other (sequences never interact: t2s_model.py:583-779 has no cross-sequence op).  Measured:
-  // 2 x 32 sequences take 2 x 450 us per step against 1100 us for 64 on the grid-wide phase kernels.  From
-  // T2S_OPT_TC_DECODE_MIN_BATCH on the tcgen05 projections of mode 3 are the faster path and the batch stays whole.
+  // 2 x 32 sequences take 2 x 403 us per step against 1001 us for 64 on the grid-wide phase kernels, 5 x 52 take 5 x 449 us
+  // against 2863 us for 256 with the tcgen05 projections of mode 3 (which the explicit modes and the test hooks still use).
   const int fit = e->max_clusters * cs::RMAX;
   const bool hooks = e->forced || e->logits_rec || e->timeline;
-  const bool whole = e->decode_mode != 5 || fit < 1 || rq->batch <= fit || hooks ||
-                     (e->tc_ok && e->tc_decode_min_batch > 0 && rq->batch >= e->tc_decode_min_batch);
+  const bool whole = e->decode_mode != 5 || fit < 1 || rq->batch <= fit || hooks;
   if (whole) {
     if (t2s_prefill(e, rq, stream)) return 1;
     int32_t n = 0;

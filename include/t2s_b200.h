@@ -150,7 +150,8 @@ int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* 
 
 enum {
   T2S_OPT_DECODE_MODE = 0,   /* 5 (default): auto = 4 when the batch fits the cluster-stream kernel (<= 8 sequences per
-                                co-resident 16-CTA cluster: 56 on a B200), else 1;
+                                co-resident 16-CTA cluster: 56 on a B200); t2s_generate runs larger batches
+                                as equal chunks that fit, one after the other; with test hooks set: else 1;
                                 4: cluster-stream kernel: thread-block clusters own sequences end to end, no grid barrier
                                    inside a step (all remaining steps of the request in ONE launch);
                                 0: one kernel per phase over all SMs, CUDA-graph replay; 1: the same phases in one

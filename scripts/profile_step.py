@@ -17,10 +17,12 @@ ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--det", type=int, default=1)
 ap.add_argument("--tc", type=int, default=0)
 ap.add_argument("--barrier-bench", action="store_true")
+ap.add_argument("--tcmin", type=int, default=-1, help="T2S_OPT_TC_DECODE_MIN_BATCH (-1: library default)")
 a = ap.parse_args()
 sd = synthetic.make_state_dict(seed=0, eos_scale=0.0)
 eng = gsb.T2SEngine(synthetic.S1V2_CONFIG); eng.load_state_dict(sd, pe=synthetic.sine_pe())
 eng.set_option(_lib.OPT_DECODE_MODE, a.mode); eng.set_option(_lib.OPT_PREFILL_GEMM, a.tc);
+if a.tcmin >= 0: eng.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, a.tcmin)
 if a.barrier_bench:
     for ncta in (148, 74, 37):
         for n in (1000, 10000):
