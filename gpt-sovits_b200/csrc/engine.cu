@@ -675,7 +675,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
       ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
       ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
       ok = ok && launch_gemm_tc<128>(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
-      k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+      k_prefill_attn_tc<<<dim3(e->n_qtiles, NH), 128, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
       ep = TcEpilogue{};
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;

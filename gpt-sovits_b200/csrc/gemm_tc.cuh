@@ -3,7 +3,7 @@
 //   C[M, N] = A[M, K] (bf16, row-major)  x  W[N, K]^T (bf16, row-major)   with a fused epilogue
 //
 // One CTA computes a 128 x 128 output tile.  Warp roles (256 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D boxes (128 rows x 64 k) of A and W into a 4-stage
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D boxes (128 rows x 64 k) of A and W into a 3-stage
 //            shared-memory ring, 128-byte swizzle, completion on mbarriers (expect_tx)
 //   warp 1   MMA issuer: ONE elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16)
 //            from shared-memory descriptors; the accumulator lives in TMEM (128 lanes x 128 fp32 columns);
@@ -22,7 +22,9 @@
 
 namespace t2s {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 256;
+// 3 stages x 32 KB: TWO CTAs fit on an SM (and 2 x 128 of the 512 TMEM columns), so one CTA's epilogue overlaps the other's
+// MMAs - with K = 512 a tile's main loop is only 8 k-blocks, the prologue and the epilogue are most of a CTA's life
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 256;
 template <int BN> struct TcCfg {
   static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;  // 32 KB (BN=128) / 24 KB (BN=64)
   static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -125,7 +127,7 @@ __device__ __forceinline__ void store_bf16x16(bf16* dst, const float (&x)[16]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
           TcEpilogue ep) {
   using CF = TcCfg<BN>;

@@ -259,6 +259,151 @@ __global__ void __launch_bounds__(64) k_prefill_attn(Ctx c, int layer, const QTi
   }
 }
 
+// ---- the same attention on the tensor cores (mma.sync.m16n8k16, flash-attention style) ---------------------------------
+// CTA = (64-query tile of one sequence, head), 4 warps x 16 queries.  K/V tiles of 64 keys (4 KB + 4 KB: contiguous in the
+// head-major pages) are staged with cp.async, double buffered, keys past the visible range zero-filled.
+//   S = Q K^T : A = Q (registers; bf16 hi + lo halves of the fp32 pre-scaled query, so the scores keep fp32-query
+//               precision), B = K rows straight from shared memory (chunks XOR-swizzled by position: conflict free)
+//   P -> A operand of O += P V directly from the S accumulator registers; B = V through ldmatrix.trans
+// Online softmax per query row; the prefix-LM mask is applied on the scores (text rows: keys < L; audio rows: keys <= own).
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(128) k_prefill_attn_tc(Ctx c, int layer, const QTile* tiles, const int* text_len) {
+  const QTile qt = tiles[blockIdx.x];
+  const int head = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int L = text_len[qt.slot];
+  __shared__ __align__(128) unsigned char kv[2][8192];  // [buffer][K: 64 keys x 64 B | V: 64 keys x 64 B]
+  const int last = qt.q0 + qt.n_q - 1;
+  const int kv_end = (qt.q0 < L) ? max(L, last + 1) : last + 1;
+  const int ntile = (kv_end + 63) >> 6;
+  const bf16* kbase = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)head * KV_HEAD_STRIDE;
+  const int* pt = c.page_table + qt.slot * c.max_pages;
+  auto stage = [&](int kt, int buf) {  // 512 pieces of 16 B: K 0..255, V 256..511
+    const int p0 = kt * 64;
+    const bf16* src = kbase + (size_t)pt[p0 >> PAGE_SHIFT] * KV_PAGE_STRIDE + (size_t)(p0 & (PAGE - 1)) * DH;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(kv[buf]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pc = tid + 128 * i;             // piece
+      const int key = (pc & 255) >> 2;          // 4 pieces per key
+      const bf16* sp = src + (pc >= 256 ? KV_V_OFF : 0) + (size_t)(pc & 255) * 8;
+      cp_async16_zfill(dst + pc * 16, sp, p0 + key < kv_end);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // ---- this warp's queries: rows i0 = q0 + 16*warp + g and i0 + 8
+  const int li0 = warp * 16 + g, li1 = li0 + 8;
+  const bool ok0 = li0 < qt.n_q, ok1 = li1 < qt.n_q;
+  const int i0 = qt.q0 + li0, i1 = qt.q0 + li1;
+  const int nv0 = ok0 ? ((i0 < L) ? L : i0 + 1) : kv_end, nv1 = ok1 ? ((i1 < L) ? L : i1 + 1) : kv_end;
+  uint32_t qh[2][4], ql[2][4];  // A fragments: a0 (row g, dims 2t..), a1 (row g+8), a2 (row g, dims 2t+8..), a3 (row g+8)
+  {
+    const float* q0p = c.q + (size_t)(qt.row0 + li0) * D + head * DH;
+    const float* q1p = c.q + (size_t)(qt.row0 + li1) * D + head * DH;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int d = kb * 16 + h * 8 + 2 * t;
+        const float2 a = ok0 ? *reinterpret_cast<const float2*>(q0p + d) : make_float2(0.f, 0.f);
+        const float2 b = ok1 ? *reinterpret_cast<const float2*>(q1p + d) : make_float2(0.f, 0.f);
+        const float ah0 = __bfloat162float(__float2bfloat16_rn(a.x)), ah1 = __bfloat162float(__float2bfloat16_rn(a.y));
+        const float bh0 = __bfloat162float(__float2bfloat16_rn(b.x)), bh1 = __bfloat162float(__float2bfloat16_rn(b.y));
+        qh[kb][2 * h] = pack_bf2(ah0, ah1);     ql[kb][2 * h] = pack_bf2(a.x - ah0, a.y - ah1);
+        qh[kb][2 * h + 1] = pack_bf2(bh0, bh1); ql[kb][2 * h + 1] = pack_bf2(b.x - bh0, b.y - bh1);
+      }
+  }
+  float o[4][4];
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int mi = lane >> 3, r8 = lane & 7;  // ldmatrix: lane supplies row r8 of 8x8 matrix mi
+  stage(0, 0);
+  for (int kt = 0; kt < ntile; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ntile) { stage(kt + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const unsigned char* kt_s = kv[buf];
+    const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(kv[buf]) + 4096;
+    // ---- scores
+    float s[8][4];
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[n8][i] = 0.f;
+      const int key = n8 * 8 + g, sw = (key >> 1) & 3;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kt_s + key * 64 + (((kb * 2) ^ sw) << 4) + t * 4);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kt_s + key * 64 + (((kb * 2 + 1) ^ sw) << 4) + t * 4);
+        mma_bf16_16816(s[n8], make_uint4(qh[kb][0], qh[kb][1], qh[kb][2], qh[kb][3]), b0, b1);
+        mma_bf16_16816(s[n8], make_uint4(ql[kb][0], ql[kb][1], ql[kb][2], ql[kb][3]), b0, b1);
+      }
+    }
+    // ---- mask + online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      const int j = kt * 64 + n8 * 8 + 2 * t;
+      if (j >= nv0) s[n8][0] = -INFINITY;
+      if (j + 1 >= nv0) s[n8][1] = -INFINITY;
+      if (j >= nv1) s[n8][2] = -INFINITY;
+      if (j + 1 >= nv1) s[n8][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[n8][0], s[n8][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n8][2], s[n8][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    // a tile can be entirely masked for a row (text rows past the text keys): keep the state untouched then
+    const float c0 = (mn0 == -INFINITY) ? 1.f : ex2f(m0 - mn0), c1 = (mn1 == -INFINITY) ? 1.f : ex2f(m1 - mn1);
+    const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;
+    m0 = mn0; m1 = mn1;
+    float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      s[n8][0] = ex2f(s[n8][0] - e0); s[n8][1] = ex2f(s[n8][1] - e0);
+      s[n8][2] = ex2f(s[n8][2] - e1); s[n8][3] = ex2f(s[n8][3] - e1);
+      ls0 += s[n8][0] + s[n8][1]; ls1 += s[n8][2] + s[n8][3];
+    }
+    l0 = l0 * c0 + ls0; l1 = l1 * c1 + ls1;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+    // ---- O += P V : P straight from the score registers, V through ldmatrix.trans
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const uint4 a = make_uint4(pack_bf2(s[2 * kb][0], s[2 * kb][1]), pack_bf2(s[2 * kb][2], s[2 * kb][3]),
+                                 pack_bf2(s[2 * kb + 1][0], s[2 * kb + 1][1]), pack_bf2(s[2 * kb + 1][2], s[2 * kb + 1][3]));
+      const int key = kb * 16 + (mi & 1) * 8 + r8;
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {  // dim-tile pairs (0,1), (2,3)
+        uint32_t r0, r1, r2, r3;
+        const uint32_t addr = vt_s + key * 64 + (((dp * 2 + (mi >> 1)) ^ ((key >> 1) & 3)) << 4);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+        mma_bf16_16816(o[2 * dp], a, r0, r1);
+        mma_bf16_16816(o[2 * dp + 1], a, r2, r3);
+      }
+    }
+    __syncthreads();  // everybody is done with kv[buf] before the stage of tile kt + 2 overwrites it
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    if (ok0) *reinterpret_cast<uint32_t*>(c.attn + (size_t)(qt.row0 + li0) * D + head * DH + dt * 8 + 2 * t) = pack_bf2(o[dt][0] * inv0, o[dt][1] * inv0);
+    if (ok1) *reinterpret_cast<uint32_t*>(c.attn + (size_t)(qt.row0 + li1) * D + head * DH + dt * 8 + 2 * t) = pack_bf2(o[dt][2] * inv1, o[dt][3] * inv1);
+  }
+}
+
 // ---- results: prompt ++ kept tokens, original batch order (t2s_model.py:733,753,779) -----------------
 __global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_stride, long long* out,
                            long long row_stride, int* idx_out) {
