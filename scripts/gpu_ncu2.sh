@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the decode kernel only (launch list of the bench command + --set full of the decode launch)
 mkdir -p gpurun_out
-KREG='regex:k_decode_cluster|k_decode_persistent|k_gemm_tc|k_prefill_attn|k_ln_rows|k_phase|k_embed_rows|k_bert|k_init_session|k_finalize|k_rows_stats'
+KREG='regex:k_decode_cluster|k_decode_persistent|k_gemm_tc|k_prefill_attn|k_prefill_attn_tc|k_ln_rows|k_phase|k_embed_rows|k_bert|k_init_session|k_finalize|k_rows_stats'
 python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/bench_plain_for_ncu.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name "$KREG" -c 1200 --csv \
     --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_launches.log 2>&1
