@@ -884,7 +884,7 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
         CS_TL();
         // ---- sampler: CTA `rank` takes the cluster's sequence `rank`
         if ((int)rank < R) {
-          stopped = sample_row<1>(c, (int)rank * ncl + cid, step, ss);
+          stopped = sample_row<1>(c, (int)rank * ncl + cid, step, ss, sm.row_slot[rank]);
           if (stopped && tid == 0) c.seg_cnt[step % 3] = 1;
         }
       }

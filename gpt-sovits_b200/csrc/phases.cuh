@@ -690,7 +690,7 @@ __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV],
         unsigned run = exc;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (run < (unsigned)k && run + cnt[j] >= (unsigned)k) { sm.bcast[0] = 255 - 8 * lane - j; sm.bcast[1] = k - run; }
+          if (run < (unsigned)k && run + cnt[j] >= (unsigned)k) { sm.bcast[0] = 255 - 8 * lane - j; sm.bcast[1] = k - run; sm.bcast[2] = (int)cnt[j]; }
           run += cnt[j];
         }
       }
@@ -699,6 +699,26 @@ __device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&key)[SV],
     prefix |= (uint32_t)sm.bcast[0] << shift;
     mask |= 0xFFu << shift;
     k = sm.bcast[1];
+    const int left = sm.bcast[2];  // keys that share the prefix found so far
+    if (pass < 3 && left <= 32) {
+      // Few candidates left (typical after two passes: logits that agree in their leading 16 bits): gather them and let
+      // every warp rank them with shuffles - the k-th largest VALUE is the candidate with (#greater) < k <= (#greater-or-equal).
+      cta_sync<SB>();
+      if (tid == 0) sm.bcast[3] = 0;
+      cta_sync<SB>();
+#pragma unroll
+      for (int j = 0; j < SV; ++j)
+        if (valid[j] && (key[j] & mask) == prefix) sm.hist[atomicAdd(reinterpret_cast<unsigned*>(&sm.bcast[3]), 1u)] = key[j];
+      cta_sync<SB>();
+      const uint32_t ck = lane < left ? sm.hist[lane] : 0u;
+      int gt = 0, ge = 0;
+      for (int i = 0; i < left; ++i) {
+        const uint32_t o = __shfl_sync(0xffffffffu, ck, i);
+        gt += o > ck; ge += o >= ck;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, lane < left && gt < k && k <= ge);
+      return __shfl_sync(0xffffffffu, ck, __ffs(hit) - 1);
+    }
   }
   return prefix;
 }
@@ -779,28 +799,31 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
 }
 
 template <int SB>
-__device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm) {  // returns: the sequence stopped at this step
+// slot_hint >= 0: the caller already knows the row's slot (saves a dependent global load in front of everything else)
+__device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm, int slot_hint = -1) {  // returns: the sequence stopped at this step
   const int tid = threadIdx.x;
   const int width = (step < c.eos_window) ? (V - 1) : V;
   {
-    const int slot = ld_cg_i(c.active + r);
+    const int slot = slot_hint >= 0 ? slot_hint : ld_cg_i(c.active + r);
     float v[SV];
     bool valid[SV];
+    uint32_t sw[SV];  // the "seen" words of the repetition penalty: requested together with the logits (one L2 round trip)
+    const uint32_t* seen = c.seen + (size_t)slot * SEEN_WORDS;
 #pragma unroll
     for (int j = 0; j < SV; ++j) {
       const int i = tid + NT * j;
       valid[j] = i < width;
       v[j] = valid[j] ? ld_cg_f(c.logits + (size_t)r * VPAD + i) : -INFINITY;
+      sw[j] = (valid[j] && c.rep_pen != 1.0f) ? __ldcg(seen + (i >> 5)) : 0u;
       if (c.logits_rec && step < c.n_logits_rec && i < V)
         c.logits_rec[((size_t)step * c.B0 + slot) * V + i] = ld_cg_f(c.logits + (size_t)r * VPAD + i);
     }
     // repetition penalty over every distinct previous token (prompt + generated), utils.py:159-167
     if (c.rep_pen != 1.0f) {
-      const uint32_t* seen = c.seen + (size_t)slot * SEEN_WORDS;
 #pragma unroll
       for (int j = 0; j < SV; ++j) {
         const int i = tid + NT * j;
-        if (valid[j] && ((__ldcg(seen + (i >> 5)) >> (i & 31)) & 1u)) v[j] = (v[j] < 0.f) ? v[j] * c.rep_pen : v[j] / c.rep_pen;
+        if (valid[j] && ((sw[j] >> (i & 31)) & 1u)) v[j] = (v[j] < 0.f) ? v[j] * c.rep_pen : v[j] / c.rep_pen;
       }
     }
     // argmax of the penalised logits: the reference's EOS test (t2s_model.py:721/:901)
@@ -841,7 +864,9 @@ __device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm) {  // re
 #pragma unroll
       for (int j = 0; j < SV; ++j) {
         const int i = tid + NT * j;
-        if (!valid[j]) continue;
+        // tokens outside the top-k / top-p set have probability 0 and can never win the race: no random number needed
+        // (the winner is the same as if every element had drawn one)
+        if (!valid[j] || e[j] == 0.f) continue;
         uint32_t w[4];
         philox4x32_10((uint32_t)(i >> 2), (uint32_t)step, (uint32_t)(slot + c.slot_base), 0u, c.seed_lo, c.seed_hi, w);
         const uint32_t word = w[i & 3];
