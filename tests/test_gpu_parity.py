@@ -484,6 +484,32 @@ def test_large_batch_runs_as_cluster_stream_chunks(engine):
     assert len({tuple(r1.tokens[b, P:P + n].tolist()) for b in range(B)}) > B // 2
 
 
+def test_engine_from_checkpoint(tmp_path, pe_table):
+    """Checkpoint file (the reference's fp16 {"weight","config","info"} format) -> engine gives the same greedy tokens as the
+    same weights handed over as a state_dict."""
+    import gpt_sovits_b200 as gsb
+    cfg = {"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=4)}
+    sd = {k: v.half().float() for k, v in synthetic.make_state_dict(seed=11, config=cfg).items()}  # fp16-representable
+    path = str(tmp_path / "s1.ckpt")
+    torch.save({"weight": {"model." + k: v.half() for k, v in sd.items()}, "config": dict(cfg, data={"max_sec": 54}), "info": "t"}, path)
+    ids, lens, prompt, bert = synthetic.make_inputs(3, [20, 31, 26], 24, seed=2)
+    ids, bert, prompt = [t.cuda() for t in ids], [t.cuda() for t in bert], prompt.cuda()
+    kw = dict(top_k=1, early_stop_num=10, eos_suppress_steps=1)
+    eng, config = gsb.engine_from_checkpoint(path, pe=pe_table)
+    try:
+        assert config["data"]["max_sec"] == 54
+        a = eng.infer(ids, bert, prompt, **kw)
+    finally:
+        eng.close()
+    ref = gsb.T2SEngine(cfg)
+    try:
+        ref.load_state_dict(sd, pe=pe_table)
+        b = ref.infer(ids, bert, prompt, **kw)
+    finally:
+        ref.close()
+    assert a.idx == b.idx and torch.equal(a.tokens, b.tokens)
+
+
 def test_drop_in_patch_with_fake_tts_caller(weights_seed0, pe_table):
     """The class-level patch, driven the way TTS.run drives the reference (TTS.py:1042-1047, 1210-1227,
     1259): instance-level rebinding to the batched variant, prompt as an .expand view, fp16 BERT

@@ -125,3 +125,35 @@ def test_sharded_infer_gloo_world2():
     assert len(c0) == 1 and len(c1) == 1 and sorted(c0[0] + c1[0]) == list(range(7)) and not set(c0[0]) & set(c1[0])
     for i in range(7):
         assert y0[i] == (np.arange(3 + i) * (i + 1)).tolist() and i0[i] == i % 5 + 1
+
+
+def _write_ckpt(path, n_layer=2, drop=None, model_overrides=None):
+    cfg = {"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=n_layer, linear_units=2048, random_bert=0), "data": {"max_sec": 54}}
+    if model_overrides:
+        cfg["model"].update(model_overrides)
+    sd = synthetic.make_state_dict(seed=3, config={"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=n_layer)})
+    weight = {"model." + k: v.half() for k, v in sd.items() if k != drop}  # fp16 + Lightning prefix, as process_ckpt.py writes
+    torch.save({"weight": weight, "config": cfg, "info": "GPT-e1"}, path)
+    return sd
+
+
+def test_checkpoint_reader(tmp_path):
+    """The s1 checkpoint wire format of the reference (process_ckpt.py:12-17, read by TTS.py:585-599): prefix stripped,
+    shapes validated, unsupported architectures and incomplete files rejected with a clear message."""
+    import gpt_sovits_b200 as gsb
+    p = str(tmp_path / "s1.ckpt")
+    sd = _write_ckpt(p)
+    config, got = gsb.read_checkpoint(p)
+    assert config["data"]["max_sec"] == 54 and config["model"]["n_layer"] == 2
+    assert set(got) >= set(sd)
+    assert got["h.layers.1.linear1.weight"].dtype == torch.float16
+    torch.testing.assert_close(got["ar_predict_layer.weight"].float(), sd["ar_predict_layer.weight"].half().float())
+    _write_ckpt(p, drop="h.layers.1.norm2.bias")
+    with pytest.raises(ValueError, match="norm2.bias"):
+        gsb.read_checkpoint(p)
+    _write_ckpt(p, model_overrides={"hidden_dim": 1024, "embedding_dim": 1024})
+    with pytest.raises(ValueError, match="hidden_dim"):
+        gsb.read_checkpoint(p)
+    torch.save({"something": 1}, p)
+    with pytest.raises(ValueError, match="not an s1 checkpoint"):
+        gsb.read_checkpoint(p)
