@@ -422,10 +422,11 @@ def test_large_batch_tcgen05_decode(engine):
     assert int(res_tc.stats["decode_steps"]) == int(res_pk.stats["decode_steps"]) == max(res_tc.idx)
 
 
-@pytest.mark.parametrize("B,P,lo,hi", [(20, 30, 16, 48), (56, 140, 100, 260)])
+@pytest.mark.parametrize("B,P,lo,hi", [(20, 30, 16, 48), (56, 140, 100, 260), (3, 1900, 380, 400)])
 def test_cluster_stream_multi_row_vs_phase_kernels(engine, B, P, lo, hi):
     """The cluster-stream kernel with several sequences per cluster (3 and 8 rows per 16-CTA cluster; the second case also
-    crosses 128-position K/V page boundaries: up to 3 pages per sequence, partial last pages) against the grid-wide phase
+    crosses 128-position K/V page boundaries: up to 3 pages per sequence, partial last pages; the third has 18 pages per
+    sequence: several pages per warp and ring slot) against the grid-wide phase
     kernels on the same teacher-forced run with EOS forced at different steps: logits within the tolerance, identical
     retirement (idx) and tokens."""
     from gpt_sovits_b200 import _lib
@@ -448,7 +449,7 @@ def test_cluster_stream_multi_row_vs_phase_kernels(engine, B, P, lo, hi):
     res_pk = engine.infer(ids, bert, prompt, **kw)
     assert int(res_pk.stats["decode_mode"]) == 1
     assert res_cs.idx == res_pk.idx
-    assert len(set(res_cs.idx)) > 3
+    assert len(set(res_cs.idx)) > min(3, B - 2)
     a, b_ = res_cs.logits.cpu().numpy(), res_pk.logits.cpu().numpy()
     assert np.array_equal(np.isnan(a), np.isnan(b_))
     d = float(np.nanmax(np.abs(a[:, :, :1024] - b_[:, :, :1024])))
