@@ -900,8 +900,10 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
       } else {
         // nobody stopped: every sequence moves on by one position (what phase_plan would have computed)
         if ((int)rank < R && tid == 0) {
-          const int slot = sm.row_slot[rank], pos = sm.row_pos[rank] + 1;
+          const int slot = sm.row_slot[rank], pos = sm.row_pos[rank] + 1, r = (int)rank * ncl + cid;
           c.seq_len[slot] = pos + 1;
+          c.row_pos[r] = pos;  // kept current for the next launch of a sliced decode (t2s_decode with a step budget)
+          c.row_kvoff[r] = kv_row_off(sm.pt[rank][pos >> PAGE_SHIFT], pos & (PAGE - 1));
           atomicAdd(c.stats + 0, (unsigned long long)(pos + 1));
         }
         if (blockIdx.x == 0 && tid == 0) {

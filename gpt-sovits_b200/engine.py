@@ -244,6 +244,24 @@ class T2SEngine:
                 res.sampled = samp
         return res
 
+    def decode_more(self, max_new_steps: int = -1) -> int:
+        """Continue the resident session (after ``infer(..., max_new_steps=k)``) for at most ``max_new_steps`` further
+        steps; returns the steps executed.  With ``result()`` this is the streaming form: sequences that have stopped can be
+        handed to the vocoder while the others keep decoding (the reference's return_fragment mode, TTS.py:1049-1053)."""
+        n = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.t2s_decode(self._h, int(max_new_steps), self._stream(), C.byref(n)))
+        return int(n.value)
+
+    def result(self, batch: int, prompt_len: int, max_steps: int = MAX_STEPS) -> InferResult:
+        """Tokens / idx of the resident session as they stand (idx = -1: still decoding)."""
+        width = prompt_len + int(max_steps)
+        idx = (C.c_int32 * batch)()
+        with torch.cuda.device(self.device):
+            tokens = torch.empty((batch, width), dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.t2s_result(self._h, C.c_void_p(tokens.data_ptr()), width, 0, idx, self._stream()))
+        return InferResult(tokens=tokens, idx=[int(v) for v in idx], prompt_len=prompt_len, stats=self.stats())
+
     def stats(self) -> Dict[str, float]:
         s = _lib.Stats()
         _lib.check(self.lib.t2s_get_stats(self._h, C.byref(s)))

@@ -511,6 +511,41 @@ def test_engine_from_checkpoint(tmp_path, pe_table):
     assert a.idx == b.idx and torch.equal(a.tokens, b.tokens)
 
 
+def test_streaming_decode_in_slices(golden_dir, pe_table):
+    """The streaming form (t2s_decode with a step budget + t2s_result in between): sequences that stop early are reported
+    while the others keep decoding, every relaunch of the cluster-stream kernel picks the session up where it stopped, and
+    the final result equals the one-shot call.  (EOS-prone weights: sequences retire at different steps.)"""
+    from gpt_sovits_b200 import T2SEngine
+    g = _golden(golden_dir, "retire_b6")
+    sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), eos_scale=float(g["eos_scale"]))
+    eng = T2SEngine(synthetic.S1V2_CONFIG, device="cuda:0")
+    try:
+        eng.load_state_dict(sd, pe=pe_table)
+        ids, bert, prompt = _inputs(g)
+        P = int(g["prompt_len"])
+        kw = dict(top_k=1, early_stop_num=60, eos_suppress_steps=1)
+        whole = eng.infer(ids, bert, prompt, **kw)
+        assert int(whole.stats["decode_mode"]) == 4
+        part = eng.infer(ids, bert, prompt, max_new_steps=7, **kw)
+        seen_done = [i >= 0 for i in part.idx]
+        slices = 1
+        while not all(i >= 0 for i in part.idx):
+            assert eng.decode_more(7) > 0
+            part = eng.result(len(ids), P)
+            for b, i in enumerate(part.idx):
+                assert not (seen_done[b] and i < 0)  # finished stays finished
+                seen_done[b] = seen_done[b] or i >= 0
+            slices += 1
+            assert slices < 40
+        assert slices > 2
+        assert part.idx == whole.idx
+        for b in range(len(ids)):
+            n = P + max(whole.idx[b], 0)
+            assert torch.equal(part.tokens[b, :n], whole.tokens[b, :n])
+    finally:
+        eng.close()
+
+
 def test_drop_in_patch_with_fake_tts_caller(weights_seed0, pe_table):
     """The class-level patch, driven the way TTS.run drives the reference (TTS.py:1042-1047, 1210-1227,
     1259): instance-level rebinding to the batched variant, prompt as an .expand view, fp16 BERT
