@@ -24,7 +24,8 @@ OPT_DECODE_MODE, OPT_PREFILL_GEMM, OPT_NUM_CTAS, OPT_CHECK_STEPS, OPT_TC_DECODE_
 
 EXPORTS = ["t2s_create", "t2s_destroy", "t2s_last_error", "t2s_load_tensor", "t2s_prefill", "t2s_decode",
            "t2s_result", "t2s_generate", "t2s_set_forced_tokens", "t2s_set_logits_capture",
-           "t2s_get_sampled", "t2s_set_option", "t2s_get_stats", "t2s_sampler_test", "t2s_bench_barrier", "t2s_set_timeline"]
+           "t2s_get_sampled", "t2s_set_option", "t2s_get_stats", "t2s_sampler_test", "t2s_bench_barrier", "t2s_set_timeline",
+           "t2s_codes_to_latent"]
 
 
 class ModelConfig(C.Structure):
@@ -116,6 +117,7 @@ def load() -> C.CDLL:
                                      vp, vp, vp]
     lib.t2s_bench_barrier.argtypes = [vp, i32, i32, C.POINTER(C.c_float), vp]
     lib.t2s_set_timeline.argtypes = [vp, vp, i32, i32]
+    lib.t2s_codes_to_latent.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         if name not in ("t2s_destroy", "t2s_last_error"):
             getattr(lib, name).restype = i32

@@ -76,7 +76,7 @@ struct t2s_engine {
   size_t pool_pages = 0;
   // session buffers
   DevBuf ints, ints2, kvoff, attn_desc, x0_rows, x0_slots, x0b_rows, x0b_slots, yb1, yb2, sp1, sp2, q, attn, y1, h, y2, stat2, logits, part, seg_cnt, gen, sampled, seen, misc, bert_rows;
-  DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx;
+  DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx, latent_flag;
   Ctx cp{}, cd{};  // prefill / decode contexts
   bool session = false;
   int B = 0, P = 0, T = 0, n_text = 0, max_steps = 0;
@@ -220,7 +220,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
                     &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
-                    &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx};
+                    &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx, &e->latent_flag};
   for (DevBuf* b : bufs) b->release();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -856,6 +856,28 @@ extern "C" int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride
                          cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(idx_out, e->out_idx.p, (size_t)e->B * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int t2s_codes_to_latent(t2s_engine* e, const int64_t* codes, int32_t n, const float* codebook,
+                                   int32_t codebook_size, int32_t dim, int32_t upsample, float* out, void* stream_) {
+  if (!e) return fail("t2s_codes_to_latent: null engine");
+  if (n < 0 || codebook_size < 1 || dim < 1 || upsample < 1 || upsample > 8)
+    return fail("t2s_codes_to_latent: n=%d codebook_size=%d dim=%d upsample=%d out of range", n, codebook_size, dim, upsample);
+  if (n == 0) return 0;  // an empty utterance: nothing to write (out may be a zero-sized allocation)
+  if (!codes || !codebook || !out) return fail("t2s_codes_to_latent: null argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  if (e->latent_flag.ensure(8)) return 1;
+  CK(cudaMemsetAsync(e->latent_flag.p, 0, 4, s));
+  dim3 grid((n + 31) / 32, (dim + 31) / 32), block(32, 8);
+  k_codes_to_latent<<<grid, block, 0, s>>>(reinterpret_cast<const long long*>(codes), n, codebook, codebook_size, dim, upsample,
+                                          out, e->latent_flag.as<int>());
+  e->launches++;
+  CK(cudaGetLastError());
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, e->latent_flag.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bad) return fail("t2s_codes_to_latent: a code lies outside [0, %d) (index out of range in the codebook lookup)", codebook_size);
   return 0;
 }
 

@@ -404,6 +404,40 @@ __global__ void __launch_bounds__(128) k_prefill_attn_tc(Ctx c, int layer, const
   }
 }
 
+// ---- the first op after the path: SynthesizerTrn.decode's quantizer.decode(codes) + nearest x2 upsample --------------
+// (module/models.py:989-991; core_vq.py:195-197 dequantize = embedding lookup, :286-290 "b n d -> b d n", :359-365 sum over the
+// n_q = 1 layers).  out[d][up*t + j] = codebook[codes[t]][d]: a gather along the code axis written channels-first, so a
+// 32 x 32 tile goes through shared memory to keep both the codebook reads (along d) and the writes (along t) coalesced.
+// grid (ceil(T/32), ceil(dim/32)), block (32, 8).  Codes outside [0, n_codes) (EOS never belongs to the kept tokens) raise *bad.
+__global__ void k_codes_to_latent(const long long* __restrict__ codes, int T, const float* __restrict__ cb, int n_codes, int dim,
+                                  int up, float* __restrict__ out, int* bad) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32, lane = threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i;
+    float v = 0.f;
+    if (t < T) {
+      const long long cde = codes[t];
+      if (cde < 0 || cde >= n_codes) {
+        if (lane == 0) atomicExch(bad, 1);
+      } else if (d0 + lane < dim) {
+        v = cb[(size_t)cde * dim + d0 + lane];
+      }
+    }
+    tile[i][lane] = v;
+  }
+  __syncthreads();
+  const size_t row = (size_t)T * up;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int d = d0 + i;
+    if (d >= dim) break;
+    for (int j = lane; j < 32 * up; j += 32) {
+      const int tl = j / up;
+      if (t0 + tl < T) out[(size_t)d * row + (size_t)t0 * up + j] = tile[tl][i];
+    }
+  }
+}
+
 // ---- results: prompt ++ kept tokens, original batch order (t2s_model.py:733,753,779) -----------------
 __global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_stride, long long* out,
                            long long row_stride, int* idx_out) {

@@ -262,6 +262,24 @@ class T2SEngine:
             _lib.check(self.lib.t2s_result(self._h, C.c_void_p(tokens.data_ptr()), width, 0, idx, self._stream()))
         return InferResult(tokens=tokens, idx=[int(v) for v in idx], prompt_len=prompt_len, stats=self.stats())
 
+    def codes_to_latent(self, codes: torch.Tensor, codebook: torch.Tensor, upsample: int = 2) -> torch.Tensor:
+        """``F.interpolate(quantizer.decode(codes), size=upsample*T, mode="nearest")`` of SynthesizerTrn.decode
+        (module/models.py:989-991) on device: ``codes`` int64 ``[T]`` (or the reference's ``[1, 1, T]``), ``codebook`` fp32
+        ``[codebook_size, dim]`` -> fp32 ``[1, dim, upsample*T]``."""
+        if codes.dtype != torch.int64 or codebook.dtype != torch.float32 or codebook.dim() != 2:
+            raise TypeError("codes_to_latent: codes must be int64 and codebook a 2-d fp32 tensor")
+        if codes.dim() == 3 and (codes.shape[0] != 1 or codes.shape[1] != 1):
+            raise ValueError("codes_to_latent: codes must be [T] or [1, 1, T] (n_q = 1, one utterance)")
+        codes = codes.reshape(-1).to(self.device).contiguous()
+        codebook = codebook.to(self.device).contiguous()
+        n, dim = int(codes.numel()), int(codebook.shape[1])
+        with torch.cuda.device(self.device):
+            out = torch.empty((1, dim, upsample * n), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.t2s_codes_to_latent(self._h, C.c_void_p(codes.data_ptr()), n, C.c_void_p(codebook.data_ptr()),
+                                                    int(codebook.shape[0]), dim, int(upsample), C.c_void_p(out.data_ptr()),
+                                                    self._stream()))
+        return out
+
     def stats(self) -> Dict[str, float]:
         s = _lib.Stats()
         _lib.check(self.lib.t2s_get_stats(self._h, C.byref(s)))

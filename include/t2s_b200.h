@@ -121,6 +121,16 @@ int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride, int32_t t
 int t2s_generate(t2s_engine* e, const t2s_request* req, int64_t* tokens_out, int64_t row_stride,
                  int32_t tokens_on_host, int32_t* idx_out, void* stream);
 
+/* The first op after the path: SynthesizerTrn.decode's `quantized = self.quantizer.decode(codes)`
+ * followed by `F.interpolate(quantized, size=2*T, mode="nearest")` for the 25 Hz models (module/models.py:989-991;
+ * ResidualVectorQuantization.decode core_vq.py:359-365 with n_q = 1, VectorQuantization.decode :286-290,
+ * EuclideanCodebook.dequantize = F.embedding).  codes: n int64 semantic tokens ON DEVICE (e.g. a row of t2s_result's
+ * tokens_out, offset to its last idx_b entries as TTS.py slices `item[-idx:]`); codebook: [codebook_size, dim] fp32 on device
+ * (`quantizer.vq.layers.0._codebook.embed`); out: [dim, upsample*n] fp32 on device, out[d][upsample*t + j] =
+ * codebook[codes[t]][d].  A code outside [0, codebook_size) is an error (the reference's embedding lookup raises). */
+int t2s_codes_to_latent(t2s_engine* e, const int64_t* codes, int32_t n, const float* codebook, int32_t codebook_size,
+                        int32_t dim, int32_t upsample, float* out, void* stream);
+
 /* ---- test / measurement hooks (not part of the reference surface) ------------------------- */
 
 /* Teacher forcing: step s of slot b emits forced[b*n_steps + s] instead of the sampled token (the

@@ -162,6 +162,32 @@ def case_sampler_kat():
     print("sampler_kat:", n, "rows")
 
 
+def case_latent():
+    """quantizer.decode + nearest x2 of SynthesizerTrn.decode (module/models.py:989-991), from the reference's own
+    ResidualVectorQuantizer (module/quantize.py) on a small random codebook; lengths straddle the 32-wide kernel tiles."""
+    import torch.nn.functional as F
+
+    if ref_harness.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_harness.REFERENCE_ROOT)
+    from module.quantize import ResidualVectorQuantizer
+
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for tag, dim, bins, T in (("a", 48, 40, 7), ("b", 80, 64, 33), ("c", 32, 16, 1)):
+        q = ResidualVectorQuantizer(dimension=dim, n_q=1, bins=bins)
+        cb = torch.randn(bins, dim, generator=g)
+        q.vq.layers[0]._codebook.embed.copy_(cb)
+        codes = torch.randint(0, bins, (1, 1, T), generator=g)
+        with torch.no_grad():
+            z = q.decode(codes)
+            z = F.interpolate(z, size=int(z.shape[-1] * 2), mode="nearest")
+        out["codebook_" + tag] = cb.numpy()
+        out["codes_" + tag] = codes.numpy()
+        out["latent_" + tag] = z.numpy()
+    np.savez_compressed(os.path.join(GOLD, "latent.npz"), **out)
+    print("latent:", {k: v.shape for k, v in out.items() if k.startswith("latent")})
+
+
 def main():
     assert ref_harness.reference_available(), "run in the build container (needs /root/reference)"
     os.makedirs(GOLD, exist_ok=True)
@@ -173,6 +199,7 @@ def main():
     case_reffree_b1(model)
     case_retire_b6()
     case_sampler_kat()
+    case_latent()
 
 
 if __name__ == "__main__":

@@ -260,3 +260,15 @@ class T2SOracle:
                           repetition_penalty=repetition_penalty, early_stop_num=early_stop_num,
                           eos_window=EOS_WINDOW_BATCH, **kw)
         return r["tokens"], r["idx"]
+
+
+def codes_to_latent(codes: np.ndarray, codebook: np.ndarray, upsample: int = 2) -> np.ndarray:
+    """The first op after the path: ``quantizer.decode(codes)`` then nearest-neighbour upsampling by ``upsample``
+    (module/models.py:989-991; core_vq.py:359-365 sum over the single residual layer, :286-290 lookup + "b n d -> b d n",
+    :195-197 dequantize = F.embedding).  codes int64 [T] -> fp32 [1, dim, upsample*T]."""
+    codes = np.asarray(codes).reshape(-1)
+    if codes.size and (codes.min() < 0 or codes.max() >= codebook.shape[0]):
+        raise IndexError("index out of range in self")  # F.embedding's error
+    q = codebook[codes].astype(np.float32).T            # [dim, T]
+    # F.interpolate(mode="nearest") to an integer multiple: output position p reads input floor(p / upsample)
+    return np.repeat(q, upsample, axis=1)[None]

@@ -740,3 +740,26 @@ def test_argument_validation(engine):
     # the engine is still usable after errors
     r = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=2)
     assert r.idx == [2, 2]
+
+
+def test_codes_to_latent(engine, golden_dir):
+    """t2s_codes_to_latent against the reference-recorded goldens and the oracle: bit-exact; the model's
+    real shape (1024 codes x 768 channels, an utterance of 1500 tokens); lengths that are not tile multiples; the reference's
+    [1, 1, T] form; an out-of-range code is an error as in the reference's embedding lookup; T = 0."""
+    from oracle.t2s_oracle import codes_to_latent
+    g = np.load(os.path.join(golden_dir, "latent.npz"))
+    for tag in "abc":
+        got = engine.codes_to_latent(torch.from_numpy(g["codes_" + tag]).cuda(), torch.from_numpy(g["codebook_" + tag]).cuda())
+        assert np.array_equal(got.cpu().numpy(), g["latent_" + tag])
+    rng = np.random.default_rng(5)
+    cb = rng.standard_normal((1024, 768), dtype=np.float32)
+    cbd = torch.from_numpy(cb).cuda()
+    for T, up in ((1500, 2), (31, 2), (65, 1), (100, 3)):
+        codes = rng.integers(0, 1024, T)
+        got = engine.codes_to_latent(torch.from_numpy(codes).cuda(), cbd, upsample=up)
+        assert got.shape == (1, 768, up * T) and np.array_equal(got.cpu().numpy(), codes_to_latent(codes, cb, up))
+    assert engine.codes_to_latent(torch.zeros(0, dtype=torch.int64).cuda(), cbd).shape == (1, 768, 0)
+    with pytest.raises(RuntimeError, match="outside"):
+        engine.codes_to_latent(torch.tensor([3, 1024]).cuda(), cbd)  # EOS is never a code
+    with pytest.raises(TypeError):
+        engine.codes_to_latent(torch.tensor([3], dtype=torch.int32).cuda(), cbd)

@@ -121,3 +121,16 @@ def test_exp_noise_properties():
     assert abs(float(so.exp_noise(1, 0, 0, 200000).mean()) - 1.0) < 0.02
     assert not np.array_equal(q, so.exp_noise(1234, 3, 18, 1025))
     assert not np.array_equal(q, so.exp_noise(1234, 4, 17, 1025))
+
+
+def test_codes_to_latent_golden(golden_dir):
+    """The restated first op after the path (quantizer.decode + nearest x2, module/models.py:989-991) against outputs of the
+    reference's own ResidualVectorQuantizer + F.interpolate (oracle/make_goldens.py case_latent): bit-exact (a gather)."""
+    from oracle.t2s_oracle import codes_to_latent
+    g = np.load(os.path.join(golden_dir, "latent.npz"))
+    for tag in "abc":
+        got = codes_to_latent(g["codes_" + tag], g["codebook_" + tag], 2)
+        assert got.dtype == np.float32 and np.array_equal(got, g["latent_" + tag])
+    with pytest.raises(IndexError):
+        codes_to_latent(np.array([0, 40]), g["codebook_a"], 2)
+    assert codes_to_latent(np.zeros(0, np.int64), g["codebook_a"], 2).shape == (1, 48, 0)
