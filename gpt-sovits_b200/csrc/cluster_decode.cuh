@@ -26,6 +26,7 @@
 // All clusters read the same weight stream at about the same time, so HBM sees the weights once per step and the other
 // clusters hit L2 (126 MB).  Everything is deterministic: fixed-order reductions, no floating-point atomics.
 #pragma once
+#include <type_traits>
 #include "phases.cuh"
 
 namespace t2s {
@@ -438,9 +439,11 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[mt][i] = 0.f;
-      for (int pg = first; pg < npg; pg += NCW) {
-        const int np = min(PAGE, pos - pg * PAGE);
-        const int ntile = (np + 15) >> 4;
+      // one page; FULL = all 128 positions valid (every page but a sequence's last): the tile and position predicates fold away
+      auto page = [&](int pg, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int np = FULL ? PAGE : min(PAGE, pos - pg * PAGE);
+        const int ntile = FULL ? 8 : (np + 15) >> 4;
         const unsigned slot = ring_slot(j + pg);
         mbar_wait(&sm.kfull[slot], ring_par(j + pg));
         int nl, nr;
@@ -532,6 +535,10 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
         }
         __syncwarp();
         if (lane == 0 && more) kv_issue(c, sm, j + pg + NSLOT, nl, nr, rank, true);  // V half is free: next page's V
+      };
+      for (int pg = first; pg < npg; pg += NCW) {
+        if (pos - pg * PAGE >= PAGE) page(pg, std::true_type{});
+        else page(pg, std::false_type{});
       }
       // the quads hold disjoint positions: sum l over g (every column of O already covers all positions of the pages)
       l += __shfl_xor_sync(0xffffffffu, l, 4);
