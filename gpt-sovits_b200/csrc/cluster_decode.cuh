@@ -370,14 +370,6 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint4& r) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-// round-to-nearest-even to bf16 with integer ops (finite inputs; the conversion instruction runs on the quarter-rate pipe
-// that the exponentials already saturate)
-__device__ __forceinline__ float bf16_round_fast(float x) {
-  const uint32_t u = __float_as_uint(x);
-  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
-}
-// two floats that are already bf16-representable -> packed bf16x2 (lo = a, hi = b)
-__device__ __forceinline__ uint32_t pack_bf2_exact(float a, float b) { return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632); }
 
 // The K/V pages a CTA reads in one step, in consumption order: layer-major, then sequence, then page.  Page q of the step
 // has ring index base + q; ring index i lives in slot i % 8, which belongs to warp i % 8.
@@ -486,11 +478,11 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
         const float corr = fast_exp2(m - mn);
         m = mn;
         float ls = 0.f;
+        uint32_t pw[8];  // the probabilities of positions (g, g + 8) of tile pt, rounded to bf16 and packed (lo, hi)
 #pragma unroll
         for (int pt = 0; pt < 8; ++pt) {
-          sc[pt][0] = bf16_round_fast(fast_exp2(sc[pt][0] - mn));
-          sc[pt][1] = bf16_round_fast(fast_exp2(sc[pt][1] - mn));
-          ls += sc[pt][0] + sc[pt][1];
+          pw[pt] = pack_bf2(fast_exp2(sc[pt][0] - mn), fast_exp2(sc[pt][1] - mn));  // one cvt.rn.bf16x2 per pair
+          ls += __uint_as_float(pw[pt] << 16) + __uint_as_float(pw[pt] & 0xFFFF0000u);  // the row sum of what the MMA multiplies
         }
         l = l * corr + ls;  // this lane's positions only (g, g+8 of every tile); the quads are summed once per sequence
 #pragma unroll
@@ -503,9 +495,9 @@ __device__ __forceinline__ void attention_rows(const Ctx& c, Smem& sm, const KvS
           uint32_t pb[8][2];
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
-            const float pa = __shfl_sync(0xffffffffu, sc[kb][0], 8 * t + t), pq = __shfl_sync(0xffffffffu, sc[kb][0], 8 * t + 4 + t);
-            const float pc = __shfl_sync(0xffffffffu, sc[kb][1], 8 * t + t), pd = __shfl_sync(0xffffffffu, sc[kb][1], 8 * t + 4 + t);
-            pb[kb][0] = pack_bf2_exact(pa, pq); pb[kb][1] = pack_bf2_exact(pc, pd);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, pw[kb], 8 * t + t), w1 = __shfl_sync(0xffffffffu, pw[kb], 8 * t + 4 + t);
+            pb[kb][0] = __byte_perm(w0, w1, 0x5410);  // positions 16kb + 2t, 2t+1   (the two quads' lo halves)
+            pb[kb][1] = __byte_perm(w0, w1, 0x7632);  // positions 16kb + 2t+8, 2t+9 (their hi halves)
           }
           float o2[2][4];  // second accumulator chain per output tile (odd position blocks): shorter dependent MMA chains
 #pragma unroll
