@@ -15,14 +15,17 @@
 //     hand-off wait that precedes it.  (Weights never touch shared memory: a TMA ring doubled the shared-memory traffic
 //     and bounded the GEMVs, see DESIGN.md.)
 //   * The K/V pages of the head (one contiguous 16 KB block per 128 positions: common.cuh kv_row_off) stream through an
-//     8 x 16 KB shared-memory ring fed by TMA bulk copies (one copy per page), running ahead across layers.  Ring slot i
-//     belongs to warp i: the warp consumes a page on the tensor cores and immediately issues the copy of the next page
-//     that maps to its slot, so there is no producer warp, no "empty" barrier and all 8 warps keep 255 registers.
+//     8 x 16 KB shared-memory ring fed by TMA bulk copies (K half and V half of a page separately, exact sizes, L2
+//     evict-first), running ahead across layers.  Ring slot i belongs to warp i: the warp consumes a page on the tensor
+//     cores (mma.sync: S = K q^T, online softmax, O += P V) and issues the copies of the next page that maps to its slot as
+//     soon as each half is free, so there is no producer warp, no "empty" barrier and all 8 warps keep 254 registers.
 //   * The four hand-offs of a layer (attention out, residual sum 1, FFN hidden, residual sum 2) are all-gathers through
-//     DISTRIBUTED SHARED MEMORY: st.async writes 16-byte pieces into every peer's buffer and completes bytes on the
-//     peer's mbarrier, so data and "ready" signal travel together (~0.3 us per hand-off instead of a grid barrier).
+//     DISTRIBUTED SHARED MEMORY: every CTA stages its block once and sends it to each peer with one bulk copy
+//     (cp.async.bulk.shared::cluster) that completes bytes on the PEER's mbarrier, so data and "ready" signal travel
+//     together (0.4-1.2 us per hand-off instead of a grid barrier + L2 round trip).
 //   * Logits go through global memory to one CTA per sequence, which runs the same fused sampler as the other modes
-//     (sample_row); one grid barrier pair per STEP lets CTA 0 retire finished sequences and re-deal rows.
+//     (sample_row); ONE grid barrier per step; the retirement plan (CTA 0 compacts the active list and re-deals rows) and
+//     its second barrier only run in steps in which a sequence stopped.
 // All clusters read the same weight stream at about the same time, so HBM sees the weights once per step and the other
 // clusters hit L2 (126 MB).  Everything is deterministic: fixed-order reductions, no floating-point atomics.
 #pragma once
