@@ -86,7 +86,7 @@ struct __align__(128) Smem {
   long long row_kvoff[RMAX];
   alignas(16) float vec[2][VC_FLOATS];  // the layer's vectors (biases of the own slices, LayerNorm gamma / beta): 2-deep ring of its own
   int row_npg[RMAX];                  // cached pages per sequence this step
-  unsigned short pmap[RMAX * 32];     // page q of a layer (consumption order) -> (sequence << 8) | page
+  alignas(8) uint2 pdesc[RMAX * 32];  // page q of a layer (consumption order) -> (offset of this head's K|V block inside a layer's pool, in 16-byte units; valid bytes per half)
   unsigned long long kfull[NSLOT], vfull_kv[NSLOT], vfull[2], ebar[4], cbar;  // K half / V half of a ring slot land separately
 };
 
@@ -378,13 +378,13 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // has ring index base + q; ring index i lives in slot i % 8, which belongs to warp i % 8.
 struct KvStream { unsigned base; int total, ptot; };  // ring index of the step's first page; pages per step; pages per layer
 // lane 0 of the owning warp: start the TMA copy of ring index idx (= page `rem` of layer `layer`, rem < ptot) into its slot.
-// sm.pmap[rem] = (sequence << 8) | page was filled by the step prologue.
+// sm.pdesc[rem] (block offset, valid bytes) was filled by the step prologue: the request sits on the owning warp's critical
+// path (lane 0 alone, the other lanes wait), so everything that does not depend on the layer is computed there, once per step.
 __device__ __forceinline__ void kv_issue(const Ctx& c, Smem& sm, unsigned idx, int layer, int rem, uint32_t rank, bool v_half) {
-  const int e = sm.pmap[rem], n = e >> 8, pg = e & 0xFF;
-  const int pos = sm.row_pos[n];
-  const uint32_t bytes = (uint32_t)min(PAGE, pos - pg * PAGE) * DH * 2;  // only the valid rows (the last page is partial)
-  const bf16* src = c.kpool + (size_t)layer * c.kv_layer_stride + (size_t)rank * KV_HEAD_STRIDE + (size_t)sm.pt[n][pg] * KV_PAGE_STRIDE +
-                    (v_half ? KV_V_OFF : 0);
+  const uint2 d = sm.pdesc[rem];
+  const uint32_t bytes = d.y;  // only the valid rows (the last page is partial)
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(c.kpool + (size_t)layer * c.kv_layer_stride) + (size_t)d.x * 16 +
+                             (v_half ? KV_V_OFF * 2 : 0);
   const unsigned slot = ring_slot(idx);
   void* bar = v_half ? (void*)&sm.vfull_kv[slot] : (void*)&sm.kfull[slot];
   // The K half and the V half of a slot are copied separately: the next page's K is requested as soon as this page's scores
@@ -738,7 +738,9 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
         ks.base = cons; ks.ptot = 0;
         for (int n = 0; n < R; ++n) {
           const int npg = sm.row_npg[n];
-          for (int pg = tid; pg < npg; pg += NCW * 32) sm.pmap[ks.ptot + pg] = (unsigned short)((n << 8) | pg);
+          for (int pg = tid; pg < npg; pg += NCW * 32)
+            sm.pdesc[ks.ptot + pg] = make_uint2((uint32_t)((((size_t)sm.pt[n][pg] * KV_PAGE_STRIDE + (size_t)rank * KV_HEAD_STRIDE) * 2) >> 4),
+                                                (uint32_t)min(PAGE, sm.row_pos[n] - pg * PAGE) * DH * 2);
           ks.ptot += npg;
         }
         ks.total = ks.ptot * c.n_layer;
