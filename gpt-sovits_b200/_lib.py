@@ -8,8 +8,11 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libt2s_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in
-           ("engine.cu", "kernels.cuh", "phases.cuh", "common.cuh", "gemm_tc.cuh")]
+import glob  # noqa: E402
+
+# engine.cu is the translation unit; every header it includes (and the C-ABI header) is a rebuild dependency
+SOURCES = [os.path.join(_HERE, "csrc", "engine.cu")] + sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cuh"))) + \
+          [os.path.join(os.path.dirname(_HERE), "include", "t2s_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -594,7 +594,7 @@ struct GridBar {
         if ((++spins & 0x3FFu) == 0) {
           const long long now = clock64();
           if (t0 == 0) t0 = now;
-          if (now - t0 > 4000000000ll || __ldcg(abort_flag) != 0) { atomicExch(abort_flag, 1); break; }
+          if (now - t0 > 4000000000ll || __ldcg(abort_flag) != 0) { atomicCAS(abort_flag, 0, ABORT_WATCHDOG); break; }
         }
       }
     }
@@ -903,8 +903,12 @@ k_decode_cluster(Ctx c, const unsigned char* __restrict__ wstream, const unsigne
         fresh = true;
       } else {
         // nobody stopped: every sequence moves on by one position (what phase_plan would have computed)
+        // thread 0 publishes row `rank` from the pre-update position; thread `rank` of the same warp overwrites that entry
+        // below: read first, then a warp barrier, so independent thread scheduling cannot reorder the two
+        const int pub_pos = ((int)rank < R && tid == 0) ? sm.row_pos[rank] : 0;
+        __syncwarp();
         if ((int)rank < R && tid == 0) {
-          const int slot = sm.row_slot[rank], pos = sm.row_pos[rank] + 1, r = (int)rank * ncl + cid;
+          const int slot = sm.row_slot[rank], pos = pub_pos + 1, r = (int)rank * ncl + cid;
           c.seq_len[slot] = pos + 1;
           c.row_pos[r] = pos;  // kept current for the next launch of a sliced decode (t2s_decode with a step budget)
           c.row_kvoff[r] = kv_row_off(sm.pt[rank][pos >> PAGE_SHIFT], pos & (PAGE - 1));

@@ -56,6 +56,9 @@ __host__ __device__ constexpr int kv_feat(long long kvoff, int f) {
   return (f >> 5) * KV_HEAD_STRIDE + (((((f >> 3) & 3) ^ kv_swz_of(kvoff))) << 3) + (f & 7);
 }
 
+// abort_flag values: a lost CTA (grid-barrier watchdog) | an input / forced token id outside its embedding table
+constexpr int ABORT_WATCHDOG = 1, ABORT_BAD_ID = 2;
+
 constexpr int PART_STRIDE = 2 * NH + D;  // per attention partial: m[16], l[16], acc[512]
 
 typedef __nv_bfloat16 bf16;
@@ -76,6 +79,7 @@ struct Ctx {
   float alpha_audio, alpha_text;
   int n_layer;
   int pe_len;
+  int phoneme_vocab;  // rows of emb_text: ids are validated on device (abort_flag = ABORT_BAD_ID), like nn.Embedding's index check
   // KV cache: one pool [n_layer][n_pages][NH][K|V][PAGE][DH] bf16 (see kv_row_off; vpool = kpool + KV_V_OFF), page table [B][max_pages]
   bf16* kpool;
   bf16* vpool;
@@ -225,7 +229,7 @@ struct GridBarrier {
           long long now = clock64();
           if (t0 == 0) t0 = now;
           if (now - t0 > 4000000000ll || __ldcg(abort_flag) != 0) {  // ~2 s at 1.9 GHz
-            atomicExch(abort_flag, 1);
+            atomicCAS(abort_flag, 0, ABORT_WATCHDOG);
             break;
           }
         }

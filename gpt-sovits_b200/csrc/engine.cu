@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,11 @@
 using namespace t2s;
 
 static thread_local std::string g_err;
+// The persistent decode kernels (cluster-stream, wide) synchronise their CTAs with hand-rolled grid barriers and therefore need
+// every CTA co-resident.  Two engines of one process decoding at the same time on one GPU could each get a partial set of
+// SMs and spin until the watchdog fires, so decode launches of a process are serialised (a launch is held until its kernel
+// has finished: t2s_decode synchronises anyway).  Other PROCESSES on the same GPU are the operator's business.
+static std::mutex g_decode_mu;
 
 static int fail(const char* fmt, ...) {
   char buf[1024];
@@ -471,8 +477,11 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   if (rq->bert_dtype < 0 || rq->bert_dtype > 2) return fail("t2s_prefill: bad bert_dtype");
   if (!rq->phoneme_ids || !rq->phoneme_lens || !rq->bert || !rq->bert_stride_c || !rq->bert_stride_t)
     return fail("t2s_prefill: null input pointer");
+  // early_stop_num: -1 = off; any other value n stops once more than n tokens were sampled (t2s_model.py:747/:897:
+  // `early_stop_num != -1 and (len - prefix) > early_stop_num`), so n < -1 behaves like 0: stop at the first step
+  const int early_stop = rq->early_stop_num == -1 ? -1 : std::max(rq->early_stop_num, 0);
   int steps_cap = rq->max_steps;
-  if (rq->early_stop_num >= 0) steps_cap = std::min(steps_cap, rq->early_stop_num + 1);
+  if (early_stop >= 0) steps_cap = std::min(steps_cap, early_stop + 1);
   std::vector<int> text_len(B), text_off(B), s0(B), row0(B);
   int n_text = 0, T = 0, max_pages = 0;
   for (int b = 0; b < B; ++b) {
@@ -606,7 +615,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.head_c1 = e->head_c.as<float>(); c.head_c0 = e->head_c.as<float>() + VPAD;
   c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
   c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
-  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len;
+  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len; c.phoneme_vocab = e->cfg.phoneme_vocab;
   c.kpool = e->kpool.as<bf16>(); c.vpool = c.kpool + KV_V_OFF;
   c.kv_layer_stride = e->pool_pages * (size_t)KV_PAGE_STRIDE;
   c.page_table = e->d_page_table; c.max_pages = max_pages;
@@ -624,7 +633,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   c.attn_ctas = ((e->decode_mode == 1 || e->decode_mode == 5) && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
 
   c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
-  c.early_stop = rq->early_stop_num < 0 ? -1 : rq->early_stop_num; c.top_k = rq->top_k;
+  c.early_stop = early_stop; c.top_k = rq->top_k;
   c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
   c.seed_lo = (uint32_t)(rq->seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(rq->seed >> 32);
   c.slot_base = e->slot_base;
@@ -638,6 +647,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   // ---- launch
   CK(cudaEventRecord(e->ev0, s));
   const int g = e->num_sms;
+  CK(cudaMemsetAsync(e->cd.abort_flag, 0, 4, s));
   k_init_session<<<B, 128, 0, s>>>(e->cd, d_prompt, prompt_stride, e->d_s0);
   CK(cudaMemcpyAsync(cp.n_rows, &e->T, 4, cudaMemcpyHostToDevice, s));
   k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride);
@@ -705,7 +715,11 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);
   CK(cudaEventRecord(e->ev1, s));
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_pinned + 8, e->cd.abort_flag, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (e->h_pinned[8] == ABORT_BAD_ID)
+    return fail("t2s_prefill: index out of range: a phoneme id lies outside [0,%d) or a prompt / forced token outside [0,%d) "
+                "(the reference's nn.Embedding raises IndexError here)", e->cfg.phoneme_vocab, V);
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->st.prefill_ms = ms;
@@ -733,6 +747,7 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   int n_active = 0, step0 = 0, aborted = 0;
   if (read_state(e, s, &n_active, &step0, &aborted)) return 1;
   int budget = max_new_steps < 0 ? e->max_steps : max_new_steps;
+  std::unique_lock<std::mutex> decode_lock(g_decode_mu);  // held until the kernel has finished (read_state below synchronises)
   CK(cudaEventRecord(e->ev0, s));
   if (n_active > 0 && budget > 0) {
     int mode = e->decode_mode;
@@ -816,6 +831,8 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   CK(cudaGetLastError());
   int step1 = 0;
   if (read_state(e, s, &n_active, &step1, &aborted)) return 1;
+  decode_lock.unlock();
+  if (aborted == ABORT_BAD_ID) return fail("t2s_decode: index out of range: a forced token lies outside [0,%d)", V);
   if (aborted) return fail("t2s_decode: grid barrier watchdog fired (a CTA never arrived); results are invalid");
   unsigned long long stats1[3];
   CK(cudaMemcpyAsync(stats1, e->cd.stats, 24, cudaMemcpyDeviceToHost, s));

@@ -103,6 +103,7 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
   for (int i = tid; i < c.P; i += blockDim.x) {
     const long long t = prompt[(long long)b * prompt_row_stride + i];
     if (t >= 0 && t < V) atomicOr(&bits[t >> 5], 1u << (t & 31));
+    else atomicExch(c.abort_flag, ABORT_BAD_ID);  // nn.Embedding(1025) raises IndexError here (t2s_model.py:636)
   }
   __syncthreads();
   if (tid < SEEN_WORDS) c.seen[(size_t)b * SEEN_WORDS + tid] = bits[tid];
@@ -115,7 +116,6 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
     if (b == 0) {
       *c.n_active = c.B0;
       *c.step = 0;
-      *c.abort_flag = 0;
       c.stats[0] = c.stats[1] = c.stats[2] = 0ull;
     }
   }
@@ -131,7 +131,11 @@ __global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, co
   const int slot = c.row_slot[r], j = c.row_pos[r], L = text_len[slot];
   float* out = c.x0 + (size_t)r * D;
   if (j < L) {
-    const long long ph = phoneme_ids[text_off[slot] + j];
+    long long ph = phoneme_ids[text_off[slot] + j];
+    if (ph < 0 || ph >= c.phoneme_vocab) {  // e.g. v2 symbol ids fed to a 512-symbol v1 checkpoint: the reference raises IndexError
+      if (threadIdx.x == 0) atomicExch(c.abort_flag, ABORT_BAD_ID);
+      ph = 0;
+    }
     const bf16* er = c.emb_text + (size_t)ph * D;
     const float* pr = c.pe + (size_t)j * D;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -140,7 +144,11 @@ __global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, co
       c.x0b[(size_t)r * D + d] = __float2bfloat16_rn(v);  // text rows: overwritten with the final value by k_bert_proj
     }
   } else {
-    const long long tok = prompt[(long long)slot * prompt_row_stride + (j - L)];
+    long long tok = prompt[(long long)slot * prompt_row_stride + (j - L)];
+    if (tok < 0 || tok >= V) {
+      if (threadIdx.x == 0) atomicExch(c.abort_flag, ABORT_BAD_ID);
+      tok = 0;
+    }
     const bf16* er = c.emb_audio + (size_t)tok * D;
     const float* pr = c.pe + (size_t)(j - L) * D;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {

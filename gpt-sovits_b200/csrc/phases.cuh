@@ -879,7 +879,13 @@ __device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm, int slot
     }
     // ---- bookkeeping (t2s_model.py:718-769)
     int emit = tok;
-    if (c.forced && step < c.n_forced) emit = __ldcg(c.forced + (size_t)slot * c.n_forced + step);
+    if (c.forced && step < c.n_forced) {
+      emit = __ldcg(c.forced + (size_t)slot * c.n_forced + step);
+      if (emit < 0 || emit >= V) {  // a forced id outside the embedding table: flag it and keep the reads in range
+        if (tid == 0) atomicExch(c.abort_flag, ABORT_BAD_ID);
+        emit = 0;
+      }
+    }
     bool stop = (emit == V - 1) || (greedy == V - 1);
     if (c.early_stop != -1 && (step + 1) > c.early_stop) stop = true;
     if (step == c.max_steps - 1) stop = true;

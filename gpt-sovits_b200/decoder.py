@@ -102,13 +102,13 @@ def infer_panel_naive(self, x: torch.LongTensor, x_lens: torch.LongTensor, promp
                       temperature: float = 1.0, repetition_penalty: float = 1.35, **kwargs):
     """t2s_model.py:814-918: x [1,L], prompts [1,P] | None, bert_feature [1,1024,L] -> (y [1,P+idx], idx)."""
     _check_top_k(top_k)
-    eng = engine_for(self)
     bsz = x.shape[0]
+    if bsz != 1:  # before any engine work (the reference would run but only ever looks at row 0's stop condition)
+        raise RuntimeError("infer_panel_naive: batch size must be 1 (use infer_panel_batch_infer)")
+    eng = engine_for(self)
     r = eng.infer([x[i] for i in range(bsz)], [bert_feature[i] for i in range(bsz)], prompts, top_k=top_k,
                   top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
                   early_stop_num=early_stop_num, eos_suppress_steps=EOS_WINDOW_NAIVE, max_steps=MAX_STEPS)
-    if bsz != 1:
-        raise RuntimeError("infer_panel_naive: batch size must be 1 (use infer_panel_batch_infer)")
     y = r.sequences()[0].unsqueeze(0)
     if prompts is None:
         return y.to(torch.int32), 0

@@ -61,11 +61,14 @@ def make_state_dict(
     gres: float = 0.2,
     eos_scale: float = 1.0,
     eos_bias_dir: float = 0.0,
+    rounding: str = "bf16",
 ) -> Dict[str, torch.Tensor]:
     """fp32 tensors holding bf16-representable values, keyed like ``Text2SemanticDecoder.state_dict()``.
 
     ``eos_scale`` multiplies the EOS row of ``ar_predict_layer.weight`` (0 forbids EOS for throughput
-    runs: its logit is then exactly 0 and never wins at logit sigma ~ 1)."""
+    runs: its logit is then exactly 0 and never wins at logit sigma ~ 1).  ``rounding`` = "bf16" (default: values the
+    engine stores exactly) or "fp16" (what a real s1 checkpoint holds, TTS.py:598-599: fp16-representable values that
+    the engine has to round to bf16)."""
     cfg = (config or S1V2_CONFIG)["model"]
     d, L = cfg["hidden_dim"], cfg["n_layer"]
     ff = 4 * d  # t2s_model.py:304 (dim_feedforward = hidden*4; the yaml's linear_units is ignored)
@@ -107,6 +110,9 @@ def make_state_dict(
         # push the EOS row along the mean hidden direction so EOS fires "naturally" (config 3)
         wp[cfg["EOS"]] += eos_bias_dir / math.sqrt(d)
     sd["ar_predict_layer.weight"] = wp
+    if rounding == "fp16":
+        return {k: v.to(torch.float16).to(torch.float32).contiguous() for k, v in sd.items()}
+    assert rounding == "bf16", rounding
     return {k: bf16_round(v).contiguous() for k, v in sd.items()}
 
 

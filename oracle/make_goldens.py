@@ -14,6 +14,18 @@ Cases (weights are regenerated from the recorded seed, not stored):
   reffree_b1    infer_panel_naive with prompts=None (:849-856): y, idx(=0), logits
   sampler_kat   logits_to_probs (utils.py:147) on hand-built rows: penalty sign flip, prompt
                 duplicates, top-k ties, top-p boundary, temperature clamp
+Round 2 (the real horizons of BASELINE.json's configs; `python -m oracle.make_goldens long_b2 ...` makes only those):
+  long_b2       infer_panel_batch_infer, B=2, 300 phonemes + 600 prompt tokens (S0 = 900: 8 K/V pages, the config-5 shape),
+                greedy, 24 steps
+  long_b1       infer_panel_naive, 120 phonemes + 1350 prompt tokens (S0 = 1470), 40 steps: the KV length crosses 1500
+                (12 pages, partial last page)
+  naive_batched_b4 / naive_batched_reffree
+                infer_panel_naive_batched (:781-812), 4 ragged items on the EOS-prone head (11-step EOS window per item,
+                items stop at different idx); with prompts and with prompts=None
+  cfg2_b32      infer_panel_batch_infer at BASELINE config 2: B=32, 60..120 phonemes + 150 prompt, top_k=15 rp 1.35
+                SAMPLED by the reference (torch seed 0), 16 steps: per-step logits [32,1025] + the tokens it emitted
+  fp16w_b1      infer_panel_naive on fp16-representable (NOT bf16-representable) weights, fp32 compute: what a real s1
+                checkpoint holds; bounds the error of the engine's bf16 rounding of such weights
 """
 from __future__ import annotations
 
@@ -188,8 +200,102 @@ def case_latent():
     print("latent:", {k: v.shape for k, v in out.items() if k.startswith("latent")})
 
 
+def case_long_b2(model):
+    L = [300, 300]
+    ids, lens, prompt, bert = synthetic.make_inputs(2, L, 600, seed=12)
+    y, idx, hook = _run(model, "infer_panel_batch_infer", (ids, lens, prompt, bert),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=24, repetition_penalty=1.35, max_len=300))
+    np.savez_compressed(os.path.join(GOLD, "long_b2.npz"), weight_seed=0, input_seed=12, phoneme_lens=L, prompt_len=600,
+                        top_k=1, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=24,
+                        logits=_pad_logits(hook.logits), y=np.stack([t.numpy() for t in y]), idx=np.array(idx))
+    print("long_b2: idx", idx)
+
+
+def case_long_b1(model):
+    ids, lens, prompt, bert = synthetic.make_inputs(1, [120], 1350, seed=13)
+    y, idx, hook = _run(model, "infer_panel_naive", (ids[0][None], lens, prompt, bert[0][None]),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=40, repetition_penalty=1.35))
+    np.savez_compressed(os.path.join(GOLD, "long_b1.npz"), weight_seed=0, input_seed=13, phoneme_lens=[120],
+                        prompt_len=1350, top_k=1, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=40,
+                        logits=_pad_logits(hook.logits), y=y.numpy(), idx=idx)
+    print("long_b1: idx", idx, "y", tuple(y.shape))
+
+
+def _naive_batched(model, name, L, P, seed, stop):
+    ids, lens, prompt, bert = synthetic.make_inputs(len(L), L, P, seed=seed)
+    y, idx, hook = _run(model, "infer_panel_naive_batched", (ids, lens, prompt, bert),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=stop, repetition_penalty=1.35))
+    # the reference loops the items: hook.logits = item 0's steps, then item 1's, ... (one row each)
+    n_item = [int(t.shape[0]) - P + 1 for t in y]  # kept tokens + the stopping step
+    assert sum(n_item) == len(hook.logits), (n_item, len(hook.logits))
+    smax = max(n_item)
+    lg = np.full((smax, len(L), 1025), np.nan, np.float32)
+    sampled = np.full((len(L), smax), -1, np.int64)
+    k = 0
+    for b, n in enumerate(n_item):
+        for s in range(n):
+            t = hook.logits[k]
+            lg[s, b, : t.shape[1]] = t[0].numpy()
+            sampled[b, s] = int(hook.samples[k][0, 0])
+            k += 1
+    ymax = max(t.shape[0] for t in y)
+    ypad = np.full((len(L), ymax), -1, np.int64)
+    for i, t in enumerate(y):
+        ypad[i, : t.shape[0]] = t.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), weight_seed=3, eos_scale=1.4, input_seed=seed, phoneme_lens=L,
+                        prompt_len=P, top_k=1, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=stop,
+                        logits=lg, sampled=sampled, n_steps=np.array(n_item), y=ypad, idx=np.array(idx))
+    print(name + ": idx", idx, "steps", n_item)
+
+
+def case_naive_batched():
+    sd = synthetic.make_state_dict(seed=3, eos_scale=1.4)
+    model = ref_harness.build_reference_model(sd, synthetic.S1V2_CONFIG)
+    _naive_batched(model, "naive_batched_b4", [40, 64, 52, 33], 60, 14, 36)
+    _naive_batched(model, "naive_batched_reffree", [48, 30, 41], 0, 15, 20)
+
+
+def case_cfg2_b32(model):
+    L = synthetic.config_lens(32, 60, 120, seed=100)
+    ids, lens, prompt, bert = synthetic.make_inputs(32, L, 150, seed=200)
+    torch.manual_seed(0)
+    y, idx, hook = _run(model, "infer_panel_batch_infer", (ids, lens, prompt, bert),
+                        dict(top_k=15, top_p=1.0, temperature=1.0, early_stop_num=15, repetition_penalty=1.35, max_len=max(L)))
+    assert all(int(t.shape[0]) == 150 + 15 for t in y), [t.shape for t in y]  # nobody hit EOS inside the window
+    emitted = np.stack([np.array([int(smp[b, 0]) for smp in hook.samples]) for b in range(32)])  # [32, 16] incl. the dropped one
+    np.savez_compressed(os.path.join(GOLD, "cfg2_b32.npz"), weight_seed=0, input_seed=200, lens_seed=100, phoneme_lens=L,
+                        prompt_len=150, top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=15,
+                        logits=_pad_logits(hook.logits), emitted=emitted,
+                        y=np.stack([t.numpy() for t in y]), idx=np.array(idx))
+    print("cfg2_b32: idx", idx[:4], "...", "logits", len(hook.logits))
+
+
+def case_fp16w_b1():
+    sd = synthetic.make_state_dict(seed=0, rounding="fp16")
+    model = ref_harness.build_reference_model(sd, synthetic.S1V2_CONFIG)
+    ids, lens, prompt, bert = synthetic.make_inputs(1, [80], 150, seed=1)
+    y, idx, hook = _run(model, "infer_panel", (ids[0][None], lens, prompt, bert[0][None]),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=24, repetition_penalty=1.35))
+    np.savez_compressed(os.path.join(GOLD, "fp16w_b1.npz"), weight_seed=0, rounding="fp16", input_seed=1, phoneme_lens=[80],
+                        prompt_len=150, top_k=1, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=24,
+                        logits=_pad_logits(hook.logits), y=y.numpy(), idx=idx)
+    print("fp16w_b1: idx", idx)
+
+
+ROUND2 = ("long_b2", "long_b1", "naive_batched", "cfg2_b32", "fp16w_b1")
+
+
 def main():
     assert ref_harness.reference_available(), "run in the build container (needs /root/reference)"
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:
+        assert all(n in ROUND2 for n in only), only
+        sd = synthetic.make_state_dict(seed=0)
+        model = ref_harness.build_reference_model(sd, synthetic.S1V2_CONFIG)
+        for n in only:
+            fn = globals()["case_" + n]
+            fn(model) if n in ("long_b2", "long_b1", "cfg2_b32") else fn()
+        return
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     sd = synthetic.make_state_dict(seed=0)
@@ -200,6 +306,11 @@ def main():
     case_retire_b6()
     case_sampler_kat()
     case_latent()
+    case_long_b2(model)
+    case_long_b1(model)
+    case_naive_batched()
+    case_cfg2_b32(model)
+    case_fp16w_b1()
 
 
 if __name__ == "__main__":

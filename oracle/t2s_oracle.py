@@ -251,6 +251,21 @@ class T2SOracle:
                           eos_window=EOS_WINDOW_NAIVE, **kw)
         return r["tokens"][0][None, :], (0 if prompts is None else r["idx"][0])
 
+    def infer_panel_naive_batched(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100,
+                                  early_stop_num=-1, temperature=1.0, repetition_penalty=1.35, **kw):
+        """The reference's Python loop of infer_panel_naive over the items (t2s_model.py:781-812): lists in, lists out;
+        `prompts` [B,P] or None (every item reference-free: int tokens, idx 0)."""
+        ys, idxs = [], []
+        for i in range(len(x)):
+            y, idx = self.infer_panel_naive(np.asarray(x[i])[None], None,
+                                            None if prompts is None else np.asarray(prompts)[i][None],
+                                            np.asarray(bert_feature[i])[None], top_k=top_k, top_p=top_p,
+                                            early_stop_num=early_stop_num, temperature=temperature,
+                                            repetition_penalty=repetition_penalty, **kw)
+            ys.append(y[0])
+            idxs.append(idx)
+        return ys, idxs
+
     def infer_panel_batch_infer(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100,
                                 early_stop_num=-1, temperature=1.0, repetition_penalty=1.35, **kw):
         """Lists as in TTS.run -> (List[y_i], List[idx_i]) in original order (t2s_model.py:583-779)."""

@@ -737,6 +737,24 @@ def test_argument_validation(engine):
         engine.infer(ids, bert, prompt, top_k=1, max_steps=5000)
     with pytest.raises(RuntimeError, match="repetition_penalty"):
         engine.infer(ids, bert, prompt, top_k=1, repetition_penalty=0.0)
+    # ids outside the embedding tables: the reference's nn.Embedding raises IndexError; here the device flags it (no silent
+    # out-of-bounds read) and the call fails
+    bad_ids = [ids[0].clone(), ids[1].clone()]
+    bad_ids[1][2] = 732
+    with pytest.raises(RuntimeError, match="out of range"):
+        engine.infer(bad_ids, bert, prompt, top_k=1, early_stop_num=2)
+    bad_ids[1][2] = -1
+    with pytest.raises(RuntimeError, match="out of range"):
+        engine.infer(bad_ids, bert, prompt, top_k=1, early_stop_num=2)
+    bad_prompt = prompt.clone()
+    bad_prompt[0, 1] = 1025
+    with pytest.raises(RuntimeError, match="out of range"):
+        engine.infer(ids, bert, bad_prompt, top_k=1, early_stop_num=2)
+    with pytest.raises(RuntimeError, match="out of range"):
+        engine.infer(ids, bert, prompt, top_k=1, early_stop_num=3, forced=torch.tensor([[1, 2, 4000], [1, 2, 3]], dtype=torch.int32))
+    # early_stop_num < -1 behaves like the reference's `!= -1 and len > early_stop_num`: stop at the first step
+    r = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=-5)
+    assert r.idx == [0, 0]
     # the engine is still usable after errors
     r = engine.infer(ids, bert, prompt, top_k=1, early_stop_num=2)
     assert r.idx == [2, 2]

@@ -86,6 +86,85 @@ def test_reffree_b1(golden_dir, weights_seed0, pe_table):
     np.testing.assert_array_equal(y, g["y"])
 
 
+# ---- round 2: the real horizons (long contexts, config 2's batch, the naive-batched loop, fp16 checkpoints) ----------------
+def test_long_b2(golden_dir, weights_seed0, pe_table):
+    """S0 = 900 (300 phonemes + 600 prompt tokens, the config-5 shape): 8 K/V pages per sequence."""
+    g = _load(golden_dir, "long_b2")
+    ids, bert, prompt = _inputs(g)
+    o = T2SOracle(weights_seed0, pe_table)
+    out = o.generate(ids, bert, prompt, top_k=1, early_stop_num=int(g["early_stop_num"]),
+                     eos_window=EOS_WINDOW_BATCH, record_logits=True)
+    _check_logits(out, g, EOS_WINDOW_BATCH)
+    assert out["idx"] == [int(v) for v in g["idx"]]
+    for b in range(2):
+        np.testing.assert_array_equal(out["tokens"][b], g["y"][b])
+
+
+def test_long_b1(golden_dir, weights_seed0, pe_table):
+    """S0 = 1470 -> 1510: the KV length crosses 1500 positions (12 pages, partial last page)."""
+    g = _load(golden_dir, "long_b1")
+    ids, bert, prompt = _inputs(g)
+    o = T2SOracle(weights_seed0, pe_table)
+    out = o.generate(ids, bert, prompt, top_k=1, early_stop_num=int(g["early_stop_num"]),
+                     eos_window=EOS_WINDOW_NAIVE, record_logits=True)
+    _check_logits(out, g, EOS_WINDOW_NAIVE)
+    assert out["idx"] == [int(g["idx"])]
+    np.testing.assert_array_equal(out["tokens"][0], g["y"][0])
+
+
+@pytest.mark.parametrize("name", ["naive_batched_b4", "naive_batched_reffree"])
+def test_naive_batched(golden_dir, pe_table, name):
+    """infer_panel_naive_batched (t2s_model.py:781-812): multi-item, 11-step EOS window per item, with and without prompts."""
+    g = _load(golden_dir, name)
+    ids, bert, prompt = _inputs(g)
+    sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), eos_scale=float(g["eos_scale"]))
+    o = T2SOracle(sd, pe_table)
+    ys, idxs = o.infer_panel_naive_batched(ids, None, prompt, bert, top_k=1, top_p=1.0,
+                                           early_stop_num=int(g["early_stop_num"]), temperature=1.0, repetition_penalty=1.35)
+    assert idxs == [int(v) for v in g["idx"]]
+    for b, y in enumerate(ys):
+        ref = g["y"][b]
+        np.testing.assert_array_equal(y, ref[ref >= 0])
+    # per-step logits of every item, through the one ragged batch the CUDA path runs (same semantics: sequences never interact)
+    out = o.generate(ids, bert, prompt, top_k=1, early_stop_num=int(g["early_stop_num"]), eos_window=EOS_WINDOW_NAIVE,
+                     record_logits=True)
+    worst = 0.0
+    for s, (lg, act) in enumerate(zip(out["logits"], out["active"])):
+        w = 1024 if s < EOS_WINDOW_NAIVE else 1025
+        for r, b in enumerate(act):
+            assert s < int(g["n_steps"][b])
+            worst = max(worst, float(np.abs(lg[r, :w] - g["logits"][s, b, :w]).max()))
+    assert worst < TOL, worst
+    if prompt is not None:
+        assert len(set(idxs)) > 2  # the items stop at different steps
+
+
+def test_cfg2_b32(golden_dir, weights_seed0, pe_table):
+    """BASELINE config 2 (B=32, 60..120 phonemes + 150 prompt, top_k=15 sampled by the reference): 16 steps, teacher-forced
+    with the tokens the reference emitted."""
+    g = _load(golden_dir, "cfg2_b32")
+    ids, bert, prompt = _inputs(g)
+    o = T2SOracle(weights_seed0, pe_table)
+    out = o.generate(ids, bert, prompt, top_k=15, early_stop_num=int(g["early_stop_num"]), eos_window=EOS_WINDOW_BATCH,
+                     forced=g["emitted"], record_logits=True)
+    _check_logits(out, g, EOS_WINDOW_BATCH)
+    assert out["idx"] == [int(v) for v in g["idx"]]
+    for b in range(32):
+        np.testing.assert_array_equal(out["tokens"][b], g["y"][b])
+
+
+def test_fp16_weights(golden_dir, pe_table):
+    g = _load(golden_dir, "fp16w_b1")
+    ids, bert, prompt = _inputs(g)
+    sd = synthetic.make_state_dict(seed=0, rounding="fp16")
+    assert any(not np.array_equal(v.numpy(), synthetic.bf16_round(v).numpy()) for v in sd.values())  # NOT bf16-representable
+    o = T2SOracle(sd, pe_table)
+    out = o.generate(ids, bert, prompt, top_k=1, early_stop_num=int(g["early_stop_num"]), eos_window=EOS_WINDOW_NAIVE,
+                     record_logits=True)
+    _check_logits(out, g, EOS_WINDOW_NAIVE)
+    np.testing.assert_array_equal(out["tokens"][0], g["y"][0])
+
+
 def test_sampler_kat(golden_dir):
     g = _load(golden_dir, "sampler_kat")
     for i in range(g["logits"].shape[0]):
