@@ -23,9 +23,10 @@ from gpt_sovits_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 0.06
-# fp16 checkpoint weights rounded to bf16 by t2s_load_tensor: measured max |dlogit| 0.2 on B200 (SURVEY.md 8c measured
-# 0.24-0.37 for bf16-rounded weights at the sharper gqk=3 init); bound = 2x the measurement
-FP16_CKPT_TOL = 0.45
+# fp16 checkpoint weights rounded to bf16 by t2s_load_tensor: measured on B200 max |dlogit| = 0.041 (median 0.034) over 25
+# teacher-forced steps against the fp32 reference on the same fp16 values, i.e. inside the ordinary bf16-arithmetic noise
+# (SURVEY.md 8c's 0.24-0.37 was for the sharper gqk=3 init).  Bound = ~2x the measurement.
+FP16_CKPT_TOL = 0.09
 MODES = [1, 4, 6]  # grid-wide phases, cluster-stream, wide small-batch kernel
 
 
