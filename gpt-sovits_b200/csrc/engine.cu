@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "cluster_decode.cuh"
+#include "wide_decode.cuh"
 
 using namespace t2s;
 
@@ -73,6 +74,8 @@ struct t2s_engine {
   DevBuf wmat, wvec, whead, wbert, bbert, emb_audio, emb_text, pe, wrow;  // wrow: row-major bf16 copies for the TMA GEMM
   DevBuf wstream, hstream;  // cluster-stream decode: per-(layer, CTA rank) consumption-ordered weight streams
   int max_clusters = 0;     // co-resident 16-CTA clusters of k_decode_cluster (0: unavailable)
+  DevBuf wwide, llbuf;      // wide decode (wide_decode.cuh): packed weights by (head, tile); hand-off cells {value, tag}
+  bool wide_ok = false;     // 144 CTAs of k_decode_wide can be co-resident
   DevBuf wrow_g, wrow_head, wrow_head_g, head_c;  // gamma-folded row-major copies (Wqkv, W1 per layer; head) + head c1/c0
   bool weights_final = false;
   float alpha_audio = 1.f, alpha_text = 1.f;
@@ -162,6 +165,8 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
   rc |= e->head_c.ensure((size_t)2 * VPAD * 4);
   rc |= e->wstream.ensure((size_t)L * cs::C * cs::LAYER_BYTES);
   rc |= e->hstream.ensure((size_t)cs::C * cs::HEAD_BYTES);
+  rc |= e->wwide.ensure((size_t)L * ws::WL_BYTES + ws::WH_BYTES);
+  rc |= e->llbuf.ensure(ws::LL_CELLS * 8);
   rc |= e->x0b_slots.ensure((size_t)MAX_B * D * 2);
   rc |= e->logits.ensure((size_t)MAX_B * VPAD * 4);
   rc |= e->part.ensure((size_t)(MAX_B + 1024) * PART_STRIDE * 4);
@@ -206,6 +211,15 @@ extern "C" int t2s_create(const t2s_model_config* cfg, t2s_engine** out) {
     }
     cudaGetLastError();  // a failure here only disables decode mode 4
   }
+  {
+    // wide decode kernel: 144 CTAs (16 heads x 9), one per SM, cooperative launch
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(ws::k_decode_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ws::k_decode_wide, ws::NTW, sizeof(ws::Smem)) == cudaSuccess)
+      e->wide_ok = per_sm >= 1 && e->num_sms >= ws::G && prop.cooperativeLaunch;
+    cudaGetLastError();  // a failure here only disables decode mode 6
+    cudaMemset(e->llbuf.p, 0, ws::LL_CELLS * 8);
+  }
   e->prefill_gemm = e->tc_ok ? 1 : 0;  // tcgen05/TMEM + TMA GEMMs for prefill unless the driver entry point is missing
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -223,7 +237,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
-                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
+                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->wwide, &e->llbuf, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx, &e->latent_flag};
@@ -362,7 +376,8 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
                                          e->wrow_head_g.as<bf16>(), e->head_c.as<float>(), e->head_c.as<float>() + VPAD, V, VPAD);
   k_pack_matrix<<<592, 256, 0, s>>>(e->whead.as<bf16>(), e->wrow_head_g.as<bf16>(), T2S_BF16, VPAD, D, VT);
   cs::k_pack_stream<<<1184, 256, 0, s>>>(e->wstream.as<unsigned char>(), e->hstream.as<bf16>(), e->wrow.as<bf16>(), e->wvec.as<float>(), e->wrow_head.as<bf16>(), L);
-  e->launches += 3;
+  ws::k_pack_wide<<<1184, 256, 0, s>>>(e->wwide.as<unsigned char>(), e->wrow.as<bf16>(), e->wvec.as<float>(), e->wrow_head.as<bf16>(), L);
+  e->launches += 4;
   CK(cudaGetLastError());
   e->weights_final = true;
   return 0;
@@ -372,7 +387,7 @@ static int finalize_weights(t2s_engine* e, cudaStream_t s) {
 extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   if (!e) return fail("t2s_set_option: null engine");
   switch (opt) {
-    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 5) return fail("decode mode must be 0 .. 5"); e->decode_mode = (int)v; break;
+    case T2S_OPT_DECODE_MODE: if (v < 0 || v > 6) return fail("decode mode must be 0 .. 6"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM:
       if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
       if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
@@ -757,6 +772,12 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
     }
     if (mode == 1 && e->tc_ok && e->tc_decode_min_batch > 0 && e->B >= e->tc_decode_min_batch) mode = 3;
     if (mode == 3 && !e->tc_ok) return fail("t2s_decode: tcgen05 decode needs the TMA descriptor entry point");
+    if (mode == 6) {
+      if (!e->wide_ok) return fail("t2s_decode: wide decode unavailable (needs %d co-resident CTAs with %zu bytes of shared memory)", ws::G, sizeof(ws::Smem));
+      if (e->B > ws::RW) return fail("t2s_decode: wide decode holds at most %d sequences (got %d)", ws::RW, e->B);
+      if (e->cd.max_pages > 32) return fail("t2s_decode: wide decode supports at most 32 KV pages per sequence");
+      if (e->cfg.n_layer + 1 >= (int)ws::TAG_STRIDE) return fail("t2s_decode: wide decode supports at most %d layers", (int)ws::TAG_STRIDE - 2);
+    }
     if (mode == 4) {
       if (e->max_clusters < 1) return fail("t2s_decode: cluster-stream decode unavailable (no co-resident 16-CTA cluster)");
       if (e->B > e->max_clusters * cs::RMAX) return fail("t2s_decode: cluster-stream decode holds at most %d sequences (got %d)", e->max_clusters * cs::RMAX, e->B);
@@ -775,6 +796,15 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs::C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       lc.attrs = at; lc.numAttrs = 1;
       CK(cudaLaunchKernelEx(&lc, cs::k_decode_cluster, e->cd, (const unsigned char*)e->wstream.p, (const unsigned char*)e->hstream.p, budget));
+      e->launches++;
+    } else if (mode == 6) {
+      CK(cudaMemsetAsync(e->cd.bar, 0, 8, s));
+      Ctx c = e->cd;
+      const unsigned char* ww = e->wwide.as<unsigned char>();
+      unsigned long long* llp = e->llbuf.as<unsigned long long>();
+      int steps = budget;
+      void* args[] = {&c, &ww, &llp, &steps};
+      CK(cudaLaunchCooperativeKernel((const void*)ws::k_decode_wide, dim3(ws::G), dim3(ws::NTW), args, sizeof(ws::Smem), s));
       e->launches++;
     } else if (mode == 1) {
       int grid = e->cd.attn_ctas;
