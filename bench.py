@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """bench.py — semantic tokens/s of the T2S decode hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
-Workload (config.workload): BASELINE.json configs[1] — s1-v2 (24L/512d/16h/FFN2048, random-init
-"sensitive" synthetic weights, EOS row zeroed so every sequence runs to the cap), batch 32 utterances per
-GPU (60..120 phonemes + 150 prompt tokens), top_k=15 top_p=1.0 temperature=1.0 repetition_penalty=1.35,
-1000-step cap.  One bench "step" = one infer_panel_batch_infer call over that batch: prefill + decode +
-sampling + result (32,000 semantic tokens per GPU).
+Workload (config.workload), default cfg2_b32 = BASELINE.json configs[1]: s1-v2 (24L/512d/16h/FFN2048, random-init
+"sensitive" synthetic weights, EOS row zeroed so every sequence runs to the cap), batch 32 utterances per GPU
+(60..120 phonemes + 150 prompt tokens), top_k=15 top_p=1.0 temperature=1.0 repetition_penalty=1.35, 1000-step cap.
+One bench "step" = one infer_panel_batch_infer call over that batch: prefill + decode + sampling + result
+(32,000 semantic tokens per GPU).
 
-  value   whole-job kept tokens / device time, inputs already resident in HBM (CUDA events on the
-          launching stream, barrier + synchronize on both sides, max over ranks)
-  e2e     the same metric through the public API with HOST buffers (pinned): H2D of phoneme ids, BERT
-          features and prompt, and D2H of the token matrix + idx, inside the timed region
-  roofline  the persistent decode kernel: algorithmic bytes (bf16 weights once per step + every active
-          sequence's KV read + its new KV row) / its CUDA-event duration, against the measured HBM peak
-  cpu_baseline  the numpy oracle port of the reference path on the host cores, on a bounded sample
+  value     whole-job kept tokens / device time, inputs already resident in HBM (CUDA events on the launching stream,
+            barrier + synchronize on both sides, max over ranks)
+  e2e       the same metric through the public API with HOST buffers (pinned): H2D of phoneme ids, BERT features and
+            prompt, and D2H of the token matrix + idx, inside the timed region
+  roofline  the persistent decode kernel: algorithmic bytes (bf16 weights once per step + every active sequence's KV
+            read + its new KV row) / its CUDA-event duration, against the measured HBM peak
+  sweep     (N = 1) short runs of the other BASELINE configs on the same GPU - cfg1_b1, batch 8 / 64 / 256 (config 4),
+            cfg5_b128 - each with the decode launch time, its algorithmic bytes and roofline fraction, and prefill time
+  cfg3      BASELINE config 3 as a STRONG-scaling job: 120 ragged utterances (fixed total) with natural EOS, sharded over
+            the N ranks by gpt_sovits_b200.shard.sharded_infer (LPT by phoneme count, one all_gather_object at the end)
+  cpu_baseline  the reference path on the host cores, on a bounded sample (see cpu_arm)
 
-Multi-GPU: utterances are independent, so ranks get disjoint batches (weak scaling), no collective on
-the data path; NCCL is used only for the barrier and the max-over-ranks of the timing.
+--impl reference: the reference's own CPU implementation of the path on the box's host cores, all threads, same
+workload / metric / unit.  The unmodified reference (Text2SemanticDecoder.infer_panel_batch_infer, imported from
+/root/reference or baseline/_ref with a torchmetrics stub) is used when one of those trees exists at run time
+(kind "reference"); the GPU box has neither, so there the numpy oracle port runs (kind "port").  Every step is a
+MEASURED bounded sample - nothing is projected: the port keeps ONE resident session (prefill during warm-up) and
+each step decodes `n` further tokens for all utterances (n calibrated in the first warm-up step so that the
+whole run fits ~2 minutes); the real reference has no resumable loop, so each of its steps is one whole call with
+early_stop_num = n (prefill included, which is why its tokens/s is lower on short samples: stated in `sample`).
+
+Multi-GPU: utterances are independent, so ranks get disjoint batches (weak scaling), no collective on the data
+path; NCCL is used only for the barrier and the max-over-ranks of the timing (and cfg3's final gather).
 """
 from __future__ import annotations
 
@@ -51,10 +64,22 @@ WORKLOADS = {
     # BASELINE.json configs[0] (the reference's CPU-runnable case): B=1, greedy, 500 steps, naive path
     "cfg1_b1": dict(batch=1, lo=80, hi=80, prompt=150, top_k=1, top_p=1.0, temperature=1.0,
                     repetition_penalty=1.35, cap=500, eos_window=11),
+    # BASELINE.json configs[3]: batch sweep per GPU, config-2 sampling, 500-step cap
+    "cfg4_b8": dict(batch=8, lo=60, hi=120, prompt=150, top_k=15, top_p=1.0, temperature=1.0,
+                    repetition_penalty=1.35, cap=500, eos_window=1),
+    "cfg4_b64": dict(batch=64, lo=60, hi=120, prompt=150, top_k=15, top_p=1.0, temperature=1.0,
+                     repetition_penalty=1.35, cap=500, eos_window=1),
+    "cfg4_b256": dict(batch=256, lo=60, hi=120, prompt=150, top_k=15, top_p=1.0, temperature=1.0,
+                      repetition_penalty=1.35, cap=500, eos_window=1),
     # BASELINE.json configs[4]: long prompt stress
     "cfg5_b128": dict(batch=128, lo=300, hi=300, prompt=600, top_k=15, top_p=1.0, temperature=1.0,
                       repetition_penalty=1.35, cap=600, eos_window=1),
 }
+SWEEP = ["cfg1_b1", "cfg4_b8", "cfg4_b64", "cfg4_b256", "cfg5_b128"]
+# BASELINE.json configs[2]: ~120 sentences of a long-form text, ragged, natural EOS (EOS row of the head scaled so that
+# sequences stop on their own), fixed TOTAL work: strong scaling over the ranks
+CFG3 = dict(total=120, lo=60, hi=140, prompt=150, top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35,
+            cap=1000, eos_window=1, eos_scale=1.4, weight_seed=3)
 
 
 def workload_inputs(w, rank):
@@ -63,13 +88,13 @@ def workload_inputs(w, rank):
     return L, ids, lens, prompt, bert
 
 
-def config_dict(w, name, n_gpus):
+def config_dict(w, name, n_gpus, global_batch=None):
     return {
         "workload": f"{name}: t2s s1-v2 24L/512d/16h/FFN2048 random-init (EOS row zeroed), batch {w['batch']}/GPU, "
                     f"{w['lo']}..{w['hi']} phonemes + {w['prompt']} prompt tokens, top_k={w['top_k']} top_p={w['top_p']} "
                     f"T={w['temperature']} rp={w['repetition_penalty']}, {w['cap']}-step cap; one step = one "
                     f"infer_panel_batch_infer call (prefill+decode+sampling)",
-        "global_batch": w["batch"] * n_gpus,
+        "global_batch": w["batch"] * n_gpus if global_batch is None else global_batch,
         "steps_cap": w["cap"],
         "parallelism": f"utterance-sharded x{n_gpus}, no data-path collective",
         "l2": "no L2 flush needed: per-step working set (152 MB weights + KV of all sequences) exceeds the 126 MB L2",
@@ -128,66 +153,235 @@ class ClockSampler:
         return out
 
 
-# ---- CPU baseline (oracle port of the reference path) ------------------------------------------------------
-def cpu_sample(w, name, steps_sample, rank=0):
-    """Times the numpy oracle (oracle/t2s_oracle.py) on the same utterances with a reduced step cap.
-    Returns (tokens/s, description, cores)."""
-    from oracle.t2s_oracle import T2SOracle
+# ---- CPU arms (the reference path on the host cores) ------------------------------------------------------------------
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms use every host core."""
     cores = os.cpu_count() or 1
-    sd = synthetic.make_state_dict(seed=0, eos_scale=0.0)
-    o = T2SOracle(sd, synthetic.sine_pe())
-    L, ids, lens, prompt, bert = workload_inputs(w, rank)
-    t0 = time.perf_counter()
-    out = o.generate([t.numpy() for t in ids], [t.numpy() for t in bert], prompt.numpy(), top_k=w["top_k"],
-                     top_p=w["top_p"], temperature=w["temperature"], repetition_penalty=w["repetition_penalty"],
-                     early_stop_num=steps_sample, eos_window=w["eos_window"], seed=1)
-    dt = time.perf_counter() - t0
-    toks = sum(out["idx"])
-    # prefill is paid once per call; the full workload amortises it over `cap` steps, the sample over few.
-    # value = projection onto the full workload: B*cap / (t_prefill + cap * mean step time of the sample)
-    # (optimistic for the CPU: the sample's KV is shorter than the full run's average).
-    t_pre = out["t_prefill"]
-    t_step = (out["t_total"] - t_pre) / max(steps_sample, 1)
-    proj = w["batch"] * w["cap"] / (t_pre + w["cap"] * t_step)
-    desc = (f"numpy fp32 port of the reference path (oracle/), {name} utterances (batch {w['batch']}): prefill "
-            f"{t_pre:.1f} s + {steps_sample} decode steps at {1000 * t_step:.0f} ms/step ({toks} tokens in {dt:.1f} s "
-            f"= {toks / dt:.1f} tok/s raw); value = projection to the {w['cap']}-step workload "
-            f"B*cap/(t_prefill + cap*t_step); BLAS threads = host cores")
-    return proj, desc, cores
+    try:
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    return cores
+
+
+def find_reference_tree():
+    """The unmodified reference, if it exists at run time: /root/reference (build container) or baseline/_ref."""
+    if os.environ.get("T2S_BENCH_FORCE_PORT"):  # lets the build container exercise the GPU box's code path
+        return None
+    for root in ("/root/reference/GPT_SoVITS", os.path.join(ROOT, "baseline", "_ref", "GPT_SoVITS"),
+                 os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(root, "AR", "models", "t2s_model.py")):
+            return root
+    return None
+
+
+class CpuArm:
+    """Bounded, MEASURED samples of a workload on the host cores.  kind = "reference": each sample is one call of the
+    unmodified infer_panel_batch_infer / infer_panel with early_stop_num = n (prefill included).  kind = "port": one
+    resident numpy-oracle session, each sample = n further decode steps of every utterance."""
+
+    def __init__(self, w, name, rank=0):
+        self.w, self.name = w, name
+        self.cores = _use_all_host_threads()
+        self.tree = find_reference_tree()
+        self.kind = "reference" if self.tree else "port"
+        self.L, self.ids, self.lens, self.prompt, self.bert = workload_inputs(w, rank)
+        self.sd = synthetic.make_state_dict(seed=0, eos_scale=0.0)
+        self.n = None
+        self.session = None
+        self.t_prefill = None
+        if self.kind == "reference":
+            from oracle import ref_harness
+            ref_harness.REFERENCE_ROOT = self.tree
+            self.model = ref_harness.build_reference_model(self.sd, synthetic.S1V2_CONFIG)
+            self.quiet = ref_harness.quiet
+        else:
+            from oracle.t2s_oracle import T2SOracle
+            self.oracle = T2SOracle(self.sd, synthetic.sine_pe())
+
+    def _ref_call(self, n):
+        w = self.w
+        kw = dict(top_k=w["top_k"], top_p=w["top_p"], temperature=w["temperature"], early_stop_num=n,
+                  repetition_penalty=w["repetition_penalty"])
+        with self.quiet(), torch.no_grad():
+            if w["eos_window"] == 11:  # the naive single-utterance path (config 1)
+                y, idx = self.model.infer_panel(self.ids[0][None], self.lens, self.prompt, self.bert[0][None], **kw)
+                return int(idx)
+            ys, idxs = self.model.infer_panel_batch_infer(self.ids, self.lens, self.prompt, self.bert, max_len=max(self.L), **kw)
+            return int(sum(idxs))
+
+    def calibrate(self, n_samples, budget_s):
+        """First (untimed) contact: the port prefills its session; both kinds measure a decode step and fix n."""
+        w = self.w
+        t0 = time.perf_counter()
+        if self.kind == "port":
+            from oracle.t2s_oracle import OracleSession
+            self.session = OracleSession(self.oracle, [t.numpy() for t in self.ids], [t.numpy() for t in self.bert],
+                                         self.prompt.numpy(), top_k=w["top_k"], top_p=w["top_p"], temperature=w["temperature"],
+                                         repetition_penalty=w["repetition_penalty"], early_stop_num=w["cap"],
+                                         eos_window=w["eos_window"], seed=1)
+            self.t_prefill = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            self.session.run(3)
+            t_step = (time.perf_counter() - t1) / 3
+            per_sample = max(budget_s - self.t_prefill, 10.0) / max(n_samples, 1)
+            self.n = int(max(2, min(64, per_sample / t_step)))
+            self.n = max(1, min(self.n, (w["cap"] - 8) // max(n_samples, 1)))  # the session must outlast every sample
+        else:
+            self._ref_call(2)
+            t_a = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            self._ref_call(8)
+            t_b = time.perf_counter() - t1
+            t_step = max((t_b - t_a) / 6, 1e-4)
+            self.t_prefill = max(t_a - 2 * t_step, 0.0)
+            per_sample = budget_s / max(n_samples, 1)
+            self.n = int(max(4, min(w["cap"], (per_sample - self.t_prefill) / t_step)))
+        return self.n
+
+    def sample(self):
+        """One measured sample: (tokens, seconds)."""
+        t0 = time.perf_counter()
+        if self.kind == "port":
+            before = sum(len(g) for g in self.session.gen)
+            self.session.run(self.n)
+            toks = sum(len(g) for g in self.session.gen) - before
+            if not self.session.active or self.session.step + self.n >= self.w["cap"]:
+                self.session = None  # (never reached within the time budget; a fresh session would be needed)
+        else:
+            toks = self._ref_call(self.n)
+        return toks, time.perf_counter() - t0
+
+    def describe(self):
+        w = self.w
+        if self.kind == "port":
+            return (f"numpy fp32 port of the reference path (oracle/), {self.name} utterances (batch {w['batch']}), one resident "
+                    f"session: prefill {self.t_prefill:.1f} s (untimed, warm-up), each step = {self.n} measured decode steps of all "
+                    f"{w['batch']} utterances at KV ~{w['prompt'] + (w['lo'] + w['hi']) // 2}+ positions (the full workload's mean KV is "
+                    f"longer, so this favours the CPU); BLAS threads = host cores; /root/reference absent on this box")
+        return (f"UNMODIFIED reference ({self.tree}) Text2SemanticDecoder."
+                f"{'infer_panel' if w['eos_window'] == 11 else 'infer_panel_batch_infer'} on CPU fp32, torch threads = host cores, "
+                f"{self.name} utterances (batch {w['batch']}); each step = one whole call with early_stop_num={self.n} "
+                f"(prefill ~{self.t_prefill:.1f} s included in every step, so tokens/s is lower than on the full "
+                f"{w['cap']}-step workload where the prefill is amortised)")
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation is Python (/root/reference), which cannot
-    travel to the GPU box, so the arm times the oracle port (kind 'port') with all host threads."""
     if rank != 0:
-        return
+        return  # the CPU's throughput does not depend on the number of GPUs: rank 0 alone runs and prints
     name = args.workload
     w = WORKLOADS[name]
-    sample = args.cpu_steps
-    vals = []
-    desc, cores = "", 1
-    t_begin = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        v, desc, cores = cpu_sample(w, name, sample)
-        if i >= args.warmup:
-            vals.append(v)
-        if time.perf_counter() - t_begin > 150 and i + 1 < args.warmup + args.steps:
-            vals = vals or [v]  # keep the whole run within a few minutes
-            break
-    value = float(np.mean(vals))
+    arm = CpuArm(w, name)
+    n_samples = args.warmup + args.steps
+    arm.calibrate(n_samples, args.cpu_budget)
+    for _ in range(args.warmup):
+        arm.sample()
+    toks, secs = 0, 0.0
+    for _ in range(args.steps):
+        t, s = arm.sample()
+        toks += t
+        secs += s
+    value = toks / secs
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1000.0 * w["batch"] * w["cap"] / value, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, name, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        # the work this arm actually did: ONE rank's batch, whatever N is (tokens/s of the host cores is the comparison)
+        "config": config_dict(w, name, args.gpus, global_batch=w["batch"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rtf": TOKENS_PER_SEC_AUDIO / value,
+        "tokens_per_step": toks / args.steps,
+        "rtf": TOKENS_PER_SEC_AUDIO / (value / w["batch"]),
     }
     print(json.dumps(line))
 
 
 # ---- our arm ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(st):
+    return (st["decode_steps"] * st["weight_bytes_per_step"]
+            + st["kv_bytes_per_position"] * (st["decode_kv_positions"] + st["decode_tokens"]))
+
+
+def sweep_point(eng, name, dev, peak, reps=2):
+    """One short device-resident run of another BASELINE config: decode launch time, algorithmic bytes, roofline fraction."""
+    w = WORKLOADS[name]
+    L, ids, lens, prompt, bert = workload_inputs(w, 0)
+    ids = [t.to(dev) for t in ids]
+    bert = [t.to(dev) for t in bert]
+    prompt = prompt.to(dev)
+    kw = dict(top_k=w["top_k"], top_p=w["top_p"], temperature=w["temperature"], repetition_penalty=w["repetition_penalty"],
+              early_stop_num=w["cap"], eos_suppress_steps=w["eos_window"], max_steps=1500)
+    eng.infer(ids, bert, prompt, seed=1, **kw)  # warm-up (allocations, module load)
+    dec_ms, pre_ms, by, toks, steps, kvpos, seqsteps = 0.0, 0.0, 0.0, 0, 0, 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(reps):
+        r = eng.infer(ids, bert, prompt, seed=10 + i, **kw)
+        st = r.stats
+        dec_ms += st["decode_ms"]; pre_ms += st["prefill_ms"]; by += algorithmic_bytes(st)
+        toks += sum(max(v, 0) for v in r.idx); steps += int(st["decode_steps"])
+        kvpos += int(st["decode_kv_positions"]); seqsteps += int(st["decode_tokens"])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    achieved = by / (dec_ms / 1000.0) / 1e9
+    return {
+        "workload": name, "batch": w["batch"], "steps_cap": w["cap"], "decode_mode": int(r.stats["decode_mode"]),
+        "tokens_per_s": toks / (ms / 1000.0), "ms_per_call": ms / reps, "launch_ms": dec_ms / reps,
+        "prefill_ms": pre_ms / reps, "prefill_rows": int(r.stats["prefill_rows"]),
+        "us_per_decode_step": 1000.0 * dec_ms / max(steps, 1), "decode_steps_per_call": steps / reps,
+        "mean_kv_positions": kvpos / max(seqsteps, 1),
+        "algorithmic_bytes_per_launch": by / reps, "achieved_gbs": achieved, "frac": achieved / peak,
+    }
+
+
+def cfg3_strong(dev, rank, world, barrier):
+    """BASELINE config 3: a fixed set of 120 ragged utterances with natural EOS, sharded over the ranks (strong scaling)."""
+    from gpt_sovits_b200 import shard
+    c = CFG3
+    sd = synthetic.make_state_dict(seed=c["weight_seed"], eos_scale=c["eos_scale"])
+    eng = gsb.T2SEngine(synthetic.S1V2_CONFIG, device=dev)
+    eng.load_state_dict(sd, pe=synthetic.sine_pe())
+    L = synthetic.config_lens(c["total"], c["lo"], c["hi"], seed=300)
+    ids, lens, prompt, bert = synthetic.make_inputs(c["total"], L, c["prompt"], seed=301)
+    ids = [t.to(dev) for t in ids]
+    bert = [t.to(dev) for t in bert]
+    prompt = prompt.to(dev)
+    mine_count = [0]
+
+    def infer_fn(indices):
+        mine_count[0] = len(indices)
+        r = eng.infer([ids[i] for i in indices], [bert[i] for i in indices], prompt[indices], top_k=c["top_k"], top_p=c["top_p"],
+                      temperature=c["temperature"], repetition_penalty=c["repetition_penalty"], early_stop_num=c["cap"],
+                      eos_suppress_steps=c["eos_window"], max_steps=1500, seed=77)
+        return r.sequences(), r.idx
+
+    shard.sharded_infer(infer_fn, L, rank=rank, world=world)  # warm-up
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    y_list, idx_list = shard.sharded_infer(infer_fn, L, rank=rank, world=world)
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    wall = 1000.0 * (time.perf_counter() - t0)
+    st = eng.stats()
+    my_ms = st["prefill_ms"] + st["decode_ms"]
+    eng.close()
+    parts = shard.partition_utterances(L, world)
+    toks_by_rank = [sum(idx_list[i] for i in p) for p in parts]
+    return {"ms": ms, "wall_ms": wall, "tokens": int(sum(idx_list)), "idx_mean": float(np.mean(idx_list)), "idx_max": int(max(idx_list)),
+            "idx_min": int(min(idx_list)), "utterances_per_rank": [len(p) for p in parts], "tokens_per_rank": toks_by_rank,
+            "my_engine_ms": my_ms, "my_utterances": mine_count[0]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,8 +390,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_b32", choices=sorted(WORKLOADS))
     ap.add_argument("--decode-mode", type=int, default=5, help="5 = auto (cluster-stream kernel when the batch fits, else grid-wide phases)")
-    ap.add_argument("--cpu-steps", type=int, default=24, help="decode steps of the bounded CPU sample")
+    ap.add_argument("--cpu-budget", type=float, default=110.0, help="seconds the whole --impl reference run may take (samples are sized to fit)")
+    ap.add_argument("--cpu-sample-s", type=float, default=15.0, help="seconds of CPU work of the cpu_baseline leg of our arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the sweep of the other configs (N = 1 only)")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the config-3 strong-scaling job")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,8 +450,7 @@ def main():
             st = r.stats
             dec_ms += st["decode_ms"]
             pre_ms += st["prefill_ms"]
-            bytes_alg += (st["decode_steps"] * st["weight_bytes_per_step"]
-                          + st["kv_bytes_per_position"] * (st["decode_kv_positions"] + st["decode_tokens"]))
+            bytes_alg += algorithmic_bytes(st)
         return toks, dec_ms, pre_ms, bytes_alg, eng.stats()["kernel_launches"] - launches0
 
     # warm-up (both forms)
@@ -291,25 +487,66 @@ def main():
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         toks, toks_e, launches = int(s[0]), int(s[1]), int(s[2])
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    st_mode = eng.stats()["decode_mode"]
+
+    # ---- the other BASELINE configs on this GPU (N = 1): driver-visible numbers for configs 1, 4, 5
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        for nm in SWEEP:
+            try:
+                sweep.append(sweep_point(eng, nm, dev, peak))
+            except Exception as ex:  # a sweep point must never take the headline down
+                sweep.append({"workload": nm, "error": str(ex)[:300]})
+    eng.close()
+
+    # ---- BASELINE config 3: fixed total work over N ranks (strong scaling)
+    cfg3 = None
+    if not args.no_cfg3:
+        try:
+            c3 = cfg3_strong(dev, rank, world, barrier)
+            t3 = torch.tensor([c3["ms"], c3["my_engine_ms"]], device=dev, dtype=torch.float64)
+            tmax, tmin = t3.clone(), t3.clone()
+            if world > 1:
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            job_ms = float(tmax[0])
+            cfg3 = {
+                "workload": f"cfg3: {CFG3['total']} ragged utterances ({CFG3['lo']}..{CFG3['hi']} phonemes + {CFG3['prompt']} prompt tokens), "
+                            f"natural EOS (EOS row of the head x{CFG3['eos_scale']}, weight seed {CFG3['weight_seed']}), top_k={CFG3['top_k']} "
+                            f"rp={CFG3['repetition_penalty']}, on-device retirement; FIXED total work sharded by shard.sharded_infer",
+                "scaling": "strong", "n_gpus": world, "tokens": c3["tokens"], "job_ms": job_ms,
+                "tokens_per_s": c3["tokens"] / (job_ms / 1000.0),
+                "tokens_per_utterance": {"mean": c3["idx_mean"], "min": c3["idx_min"], "max": c3["idx_max"]},
+                "utterances_per_rank": c3["utterances_per_rank"], "tokens_per_rank": c3["tokens_per_rank"],
+                "engine_ms_slowest_rank": float(tmax[1]), "engine_ms_fastest_rank": float(tmin[1]),
+                "limiter": "the job ends with its LONGEST utterance: every rank decodes in lock-step until its last sequence "
+                           "retires, so time ~ max over ranks of the longest utterance's steps x step time, while the per-GPU "
+                           "batch shrinks to total/N (15 at N=8) where a step costs about as much as at batch 32 (latency-bound chain)",
+            }
+        except Exception as ex:
+            cfg3 = {"error": str(ex)[:300]}
+
     if rank == 0:
         value = toks / (ms / 1000.0)
         e2e = toks_e / (ms_e / 1000.0)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         achieved = bytes_alg / (dec_ms / 1000.0) / 1e9  # rank 0's persistent decode kernel
-        st_mode = eng.stats()["decode_mode"]
         traffic = None  # dram bytes of the same launch from the committed ncu --set full capture (profiles/)
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tr.get("workload") == name and int(tr.get("decode_mode", 1)) == int(st_mode):
-                traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
-        except Exception:
-            pass
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                if tr.get("workload") == name and int(tr.get("decode_mode", 1)) == int(st_mode):
+                    traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
+                    break
+            except Exception:
+                pass
         h2d = sum(t.numel() * t.element_size() for t in ids_p) + sum(t.numel() * t.element_size() for t in bert_p) \
             + prompt_p.numel() * prompt_p.element_size()
         d2h = w["batch"] * (w["prompt"] + 1500) * 8 + w["batch"] * 4
@@ -324,7 +561,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {
-                "kernel": {4: "k_decode_cluster", 1: "k_decode_persistent"}.get(int(st_mode), "decode step graph"),
+                "kernel": {4: "k_decode_cluster", 1: "k_decode_persistent", 6: "k_decode_wide"}.get(int(st_mode), "decode step graph"),
                 "decode_mode": int(st_mode),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
@@ -334,14 +571,19 @@ def main():
             },
             "prefill_ms_per_step": pre_ms / args.steps,
             "decode_ms_per_step": dec_ms / args.steps,
+            "sweep": sweep,
+            "cfg3": cfg3,
         }
         if not args.no_cpu and world == 1:
-            v, desc, cores = cpu_sample(w, name, args.cpu_steps)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            arm = CpuArm(w, name)
+            arm.calibrate(2, args.cpu_sample_s)
+            t, s = arm.sample()
+            t2, s2 = arm.sample()
+            line["cpu_baseline"] = {"value": (t + t2) / (s + s2), "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                                    "sample": arm.describe() + f"; 2 samples, {t + t2} tokens in {s + s2:.1f} s"}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

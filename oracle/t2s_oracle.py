@@ -177,67 +177,11 @@ class T2SOracle:
         """Returns dict(tokens=[per-slot int64 arrays prompt+kept], idx=[...], logits=[steps][n,1025]
         (raw, before penalty; rows in active order), active=[steps] slot lists, sampled=[B,steps],
         margins=[B,steps])."""
-        import time
-        t_start = time.perf_counter()
-        B = len(phoneme_ids)
-        P = 0 if prompt is None else int(prompt.shape[1])
-        noise_fn = noise_fn or (lambda slot, step, n: so.exp_noise(seed, slot, step, n))
-        S0 = [len(phoneme_ids[b]) + P for b in range(B)]
-        cap = max(S0) + (max_steps if early_stop_num == -1 else min(max_steps, early_stop_num + 1)) + 1
-        K = np.zeros((self.L, B, self.H, cap, self.dh), np.float32)
-        V = np.zeros_like(K)
-        hid = np.zeros((B, self.d), np.float32)
-        for b in range(B):
-            x = self.embed_text(np.asarray(phoneme_ids[b]), np.asarray(bert[b], dtype=np.float32))
-            xy = x if P == 0 else np.concatenate([x, self.embed_audio(np.asarray(prompt[b]), 0)], axis=0)
-            h, Kb, Vb = self.prefill_one(xy, len(phoneme_ids[b]), cap)
-            hid[b], K[:, b], V[:, b] = h, Kb, Vb
-        hist: List[List[int]] = [list(map(int, prompt[b])) if P else [] for b in range(B)]
-        gen: List[List[int]] = [[] for _ in range(B)]
-        idx_out = [None] * B
-        active = list(range(B))
-        lens = np.array(S0, dtype=np.int64)
-        out = dict(logits=[], active=[], sampled=np.full((B, max_steps), -1, np.int64),
-                   margins=np.ones((B, max_steps), np.float32))
-        out["t_prefill"] = time.perf_counter() - t_start
-        for step in range(max_steps):
-            logits = (hid[active] @ self.wp.T).astype(np.float32)  # [n, 1025]
-            if record_logits:
-                out["logits"].append(logits.copy())
-            out["active"].append(list(active))
-            width = self.EOS if step < eos_window else self.EOS + 1
-            still = []
-            for r, b in enumerate(active):
-                row = logits[r, :width].copy()
-                q = noise_fn(b, step, width)
-                tok, greedy, _, margin = so.sample_row(
-                    row, hist[b] + gen[b], q, temperature, top_k, top_p, repetition_penalty)
-                out["sampled"][b, step] = tok
-                out["margins"][b, step] = margin
-                if forced is not None and step < forced.shape[1]:
-                    tok = int(forced[b, step])
-                gen[b].append(tok)
-                stop = tok == self.EOS or greedy == self.EOS
-                if early_stop_num != -1 and (step + 1) > early_stop_num:
-                    stop = True
-                if step == max_steps - 1:
-                    stop = True
-                if stop:
-                    idx_out[b] = step
-                else:
-                    still.append(b)
-            active = still
-            if not active:
-                break
-            x = np.stack([self.embed_audio(np.array([gen[b][-1]]), P + step)[0] for b in active])
-            sel = np.array(active)
-            hid[sel] = self.decode_step(x, K, V, sel, lens[sel])
-            lens[sel] += 1
-        out["t_total"] = time.perf_counter() - t_start
-        out["tokens"] = [np.array(hist[b] + gen[b][: idx_out[b]], dtype=np.int64) for b in range(B)]
-        out["idx"] = [int(i) for i in idx_out]
-        out["generated"] = gen
-        return out
+        s = OracleSession(self, phoneme_ids, bert, prompt, top_k=top_k, top_p=top_p, temperature=temperature,
+                          repetition_penalty=repetition_penalty, early_stop_num=early_stop_num, eos_window=eos_window,
+                          max_steps=max_steps, seed=seed, forced=forced, record_logits=record_logits, noise_fn=noise_fn)
+        s.run()
+        return s.result()
 
     # ---- reference-shaped entry points ---------------------------------------------------------
     def infer_panel_naive(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100,
@@ -275,6 +219,98 @@ class T2SOracle:
                           repetition_penalty=repetition_penalty, early_stop_num=early_stop_num,
                           eos_window=EOS_WINDOW_BATCH, **kw)
         return r["tokens"], r["idx"]
+
+
+class OracleSession:
+    """One infer_panel* call as a resumable object: prefill at construction, then ``run(n)`` executes at most n steps of the
+    loop (t2s_model.py:701-769 / :878-914).  ``T2SOracle.generate`` is ``OracleSession(...).run()``; bench.py's CPU arms time
+    ``run(n)`` slices of one resident session so that a bounded sample measures DECODE steps, not the prefill."""
+
+    def __init__(self, o: "T2SOracle", phoneme_ids, bert, prompt, top_k=15, top_p=1.0, temperature=1.0,
+                 repetition_penalty=1.35, early_stop_num=-1, eos_window=EOS_WINDOW_BATCH, max_steps=MAX_STEPS, seed=0,
+                 forced=None, record_logits=False, noise_fn=None):
+        import time
+        self.t_start = time.perf_counter()
+        self.o = o
+        self.kw = dict(top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty)
+        self.early_stop_num, self.eos_window, self.max_steps = early_stop_num, eos_window, max_steps
+        self.forced, self.record_logits = forced, record_logits
+        B = len(phoneme_ids)
+        P = 0 if prompt is None else int(prompt.shape[1])
+        self.B, self.P = B, P
+        self.noise_fn = noise_fn or (lambda slot, step, n: so.exp_noise(seed, slot, step, n))
+        S0 = [len(phoneme_ids[b]) + P for b in range(B)]
+        cap = max(S0) + (max_steps if early_stop_num == -1 else min(max_steps, early_stop_num + 1)) + 1
+        self.K = np.zeros((o.L, B, o.H, cap, o.dh), np.float32)
+        self.V = np.zeros_like(self.K)
+        self.hid = np.zeros((B, o.d), np.float32)
+        for b in range(B):
+            x = o.embed_text(np.asarray(phoneme_ids[b]), np.asarray(bert[b], dtype=np.float32))
+            xy = x if P == 0 else np.concatenate([x, o.embed_audio(np.asarray(prompt[b]), 0)], axis=0)
+            h, Kb, Vb = o.prefill_one(xy, len(phoneme_ids[b]), cap)
+            self.hid[b], self.K[:, b], self.V[:, b] = h, Kb, Vb
+        self.hist: List[List[int]] = [list(map(int, prompt[b])) if P else [] for b in range(B)]
+        self.gen: List[List[int]] = [[] for _ in range(B)]
+        self.idx_out = [None] * B
+        self.active = list(range(B))
+        self.lens = np.array(S0, dtype=np.int64)
+        self.step = 0
+        self.out = dict(logits=[], active=[], sampled=np.full((B, max_steps), -1, np.int64),
+                        margins=np.ones((B, max_steps), np.float32))
+        self.out["t_prefill"] = time.perf_counter() - self.t_start
+
+    def run(self, n_steps: int = -1) -> int:
+        """Executes up to n_steps loop iterations (all remaining if < 0); returns how many ran."""
+        o, out = self.o, self.out
+        ran = 0
+        while self.active and self.step < self.max_steps and (n_steps < 0 or ran < n_steps):
+            step, active = self.step, self.active
+            logits = (self.hid[active] @ o.wp.T).astype(np.float32)  # [n, 1025]
+            if self.record_logits:
+                out["logits"].append(logits.copy())
+            out["active"].append(list(active))
+            width = o.EOS if step < self.eos_window else o.EOS + 1
+            still = []
+            for r, b in enumerate(active):
+                row = logits[r, :width].copy()
+                q = self.noise_fn(b, step, width)
+                tok, greedy, _, margin = so.sample_row(
+                    row, self.hist[b] + self.gen[b], q, self.kw["temperature"], self.kw["top_k"], self.kw["top_p"],
+                    self.kw["repetition_penalty"])
+                out["sampled"][b, step] = tok
+                out["margins"][b, step] = margin
+                if self.forced is not None and step < self.forced.shape[1]:
+                    tok = int(self.forced[b, step])
+                self.gen[b].append(tok)
+                stop = tok == o.EOS or greedy == o.EOS
+                if self.early_stop_num != -1 and (step + 1) > self.early_stop_num:
+                    stop = True
+                if step == self.max_steps - 1:
+                    stop = True
+                if stop:
+                    self.idx_out[b] = step
+                else:
+                    still.append(b)
+            self.active = still
+            self.step += 1
+            ran += 1
+            if not still:
+                break
+            x = np.stack([o.embed_audio(np.array([self.gen[b][-1]]), self.P + step)[0] for b in still])
+            sel = np.array(still)
+            self.hid[sel] = o.decode_step(x, self.K, self.V, sel, self.lens[sel])
+            self.lens[sel] += 1
+        return ran
+
+    def result(self):
+        import time
+        out = self.out
+        out["t_total"] = time.perf_counter() - self.t_start
+        out["tokens"] = [np.array(self.hist[b] + self.gen[b][: (self.idx_out[b] if self.idx_out[b] is not None else len(self.gen[b]))],
+                                  dtype=np.int64) for b in range(self.B)]
+        out["idx"] = [int(i) if i is not None else -1 for i in self.idx_out]
+        out["generated"] = self.gen
+        return out
 
 
 def codes_to_latent(codes: np.ndarray, codebook: np.ndarray, upsample: int = 2) -> np.ndarray:

@@ -213,3 +213,53 @@ def test_build_dependencies_cover_every_kernel_header():
     for h in os.listdir(os.path.join(ROOT, "gpt-sovits_b200", "csrc")):
         if h.endswith(".cuh"):
             assert h in deps, h
+
+
+def test_oracle_session_slices_equal_one_shot(pe_table):
+    """The resumable form of the oracle loop (used by bench.py's CPU arms and the streaming tests): run(n) slices give exactly
+    what one generate() call gives."""
+    from oracle.t2s_oracle import OracleSession, T2SOracle
+    cfg = {"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=2)}
+    sd = synthetic.make_state_dict(seed=3, config=cfg, eos_scale=2.5)
+    o = T2SOracle(sd, pe_table)
+    ids, lens, prompt, bert = synthetic.make_inputs(3, [5, 9, 7], 6, seed=8)
+    args = ([t.numpy() for t in ids], [t.numpy() for t in bert], prompt.numpy())
+    kw = dict(top_k=5, early_stop_num=25, eos_window=1, seed=11)
+    whole = o.generate(*args, **kw)
+    s = OracleSession(o, *args, **kw)
+    ran = 0
+    while s.active:
+        mid = s.result()
+        assert all((i == -1) == (b in s.active) for b, i in enumerate(mid["idx"]))
+        ran += s.run(4)
+    part = s.result()
+    assert part["idx"] == whole["idx"] and ran == max(whole["idx"]) + 1
+    for a, b in zip(part["tokens"], whole["tokens"]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_bench_cpu_arm_port_is_measured_not_projected(monkeypatch):
+    """bench.py --impl reference on a box without the reference tree (the GPU box): the port arm times real decode steps of a
+    resident session; tokens per sample = batch x n, nothing extrapolated."""
+    import bench
+    monkeypatch.setenv("T2S_BENCH_FORCE_PORT", "1")
+    w = dict(batch=2, lo=6, hi=9, prompt=8, top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, cap=40, eos_window=1)
+    monkeypatch.setattr(bench.synthetic, "make_state_dict", _small_sd)  # 2 layers keep the CPU test quick
+    arm = bench.CpuArm(w, "tiny")
+    assert arm.kind == "port" and arm.cores == (os.cpu_count() or 1)
+    n = arm.calibrate(4, 8.0)
+    assert 1 <= n <= (40 - 8) // 4
+    toks, secs = arm.sample()
+    assert toks == 2 * n and secs > 0
+    toks2, _ = arm.sample()
+    assert toks2 == 2 * n
+    assert "measured decode steps" in arm.describe() and "prefill" in arm.describe()
+
+
+def _small_sd(**kw):
+    kw = dict(kw)
+    kw["config"] = {"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=2)}
+    return _ORIG_MAKE_SD(**kw)
+
+
+_ORIG_MAKE_SD = synthetic.make_state_dict
