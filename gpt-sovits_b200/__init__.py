@@ -13,12 +13,15 @@ from .decoder import (  # noqa: F401
     infer_panel_batch_infer,
     infer_panel_naive,
     infer_panel_naive_batched,
+    infer_panel_stream,
     patch_reference,
     unpatch_reference,
 )
 from .engine import EOS_WINDOW_BATCH, EOS_WINDOW_NAIVE, MAX_STEPS, InferResult, T2SEngine  # noqa: F401
 from .checkpoint import engine_from_checkpoint, read_checkpoint  # noqa: F401
+from .batching import StreamingSession, bucket_batches, recovery_order  # noqa: F401
 
 __all__ = ["synthetic", "T2SEngine", "InferResult", "patch_reference", "unpatch_reference", "engine_for",
            "infer_panel", "infer_panel_naive", "infer_panel_naive_batched", "infer_panel_batch_infer",
-           "MAX_STEPS", "EOS_WINDOW_NAIVE", "EOS_WINDOW_BATCH", "read_checkpoint", "engine_from_checkpoint"]
+           "MAX_STEPS", "EOS_WINDOW_NAIVE", "EOS_WINDOW_BATCH", "read_checkpoint", "engine_from_checkpoint",
+           "StreamingSession", "bucket_batches", "recovery_order", "infer_panel_stream"]

@@ -113,7 +113,7 @@ struct Ctx {
   int* attn_desc;   // [attn_ctas][2] int4 {row, pbeg, pend, (j << 16) | count}, written by phase_plan
   int attn_ctas;    // grid size of the decode attention phase (fixed for the session)
   // session (indexed by slot = original batch index)
-  int B0, P, max_steps, eos_window, early_stop, top_k;
+  int B0, P, max_steps, eos_window, early_stop, top_k;  // B0 = slot capacity of the session (stride of the per-step hooks); P: this request's prompt length
   int slot_base;  // first utterance of this session inside the caller's batch (t2s_generate splits large batches): keeps the Philox streams per utterance
   float top_p, temperature, rep_pen;
   uint32_t seed_lo, seed_hi;
@@ -123,6 +123,10 @@ struct Ctx {
   int* n_active;
   int* done;
   int* out_idx;
+  // per-slot session state (continuous batching: t2s_admit adds utterances to a resident session at a later global step)
+  int* slot_step0;                      // global step at which the slot's step 0 was sampled (0 for the first request)
+  int* slot_P;                          // prompt length of the slot's request
+  const long long* const* slot_prompt;  // the slot's prompt row (caller-owned, alive for the session)
   int* gen;      // [B0][max_steps]
   int* sampled;  // [B0][max_steps]
   int* greedy_rec;  // optional [B0][max_steps]: argmax of the penalised logits (test hook)

@@ -88,9 +88,12 @@ struct t2s_engine {
   DevBuf in_ids, in_prompt, in_bert, in_bert_ptrs, out_tokens, out_idx, latent_flag;
   Ctx cp{}, cd{};  // prefill / decode contexts
   bool session = false;
-  int B = 0, P = 0, T = 0, n_text = 0, max_steps = 0;
-  const long long* prompt_dev = nullptr;
-  long long prompt_stride = 0;
+  int B = 0, P = 0, T = 0, n_text = 0, max_steps = 0;  // B: slots in use (t2s_admit grows it)
+  int cap = 0, maxP = 0, sess_max_pages = 0;           // session geometry: slot capacity, longest prompt, K/V pages per slot
+  int session_slots = 0, session_positions = 0;        // options: slots / positions per slot to reserve at t2s_prefill
+  size_t next_page = 0;
+  std::vector<int> h_page_table;
+  DevBuf page_tab, drows, slot_prompt;                 // session-persistent: page table, decode row descriptors, per-slot prompt pointers
   std::vector<int> h_text_len, h_s0;
   int n_qtiles = 0;
   // device int layout inside `ints`
@@ -237,7 +240,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
-                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->wwide, &e->llbuf, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
+                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->wwide, &e->llbuf, &e->page_tab, &e->drows, &e->slot_prompt, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx, &e->latent_flag};
@@ -394,6 +397,8 @@ extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
       e->prefill_gemm = (int)v; break;
     case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
     case T2S_OPT_TC_DECODE_MIN_BATCH: if (v < 0 || v > 100000) return fail("tc_decode_min_batch out of range"); e->tc_decode_min_batch = (int)v; break;
+    case T2S_OPT_SESSION_SLOTS: if (v < 0 || v > MAX_B) return fail("session_slots must be in [0,%d]", MAX_B); e->session_slots = (int)v; break;
+    case T2S_OPT_SESSION_POSITIONS: if (v < 0 || v > 4000) return fail("session_positions must be in [0,4000]"); e->session_positions = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
   }
@@ -477,66 +482,108 @@ static bool launch_decode_step_tc(t2s_engine* e, const Ctx& c, cudaStream_t s) {
 }
 
 // ---- prefill ---------------------------------------------------------------------------------------------
-extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) {
-  if (!e || !rq) return fail("t2s_prefill: null argument");
+static int read_state(t2s_engine* e, cudaStream_t s, int* n_active, int* step, int* aborted);
+
+// One implementation for t2s_prefill (a new session: slots [0, B)) and t2s_admit (B more utterances join the resident session
+// in slots [e->B, e->B + B) at the session's current global step: continuous batching).  The request-local arrays (row
+// descriptors of the prompt rows, text offsets, q-tiles) live in per-call buffers; what the decode loop needs across calls
+// (page table, decode row descriptors, per-slot prompt pointers, token buffers) lives in session buffers sized for the
+// session's slot capacity.
+static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bool admit) {
+  const char* who = admit ? "t2s_admit" : "t2s_prefill";
   if (check_loaded(e)) return 1;
-  cudaStream_t s = (cudaStream_t)stream_;
   if (finalize_weights(e, s)) return 1;
   const int B = rq->batch, P = rq->prompt_len;
-  if (B < 1 || B > e->cfg.max_batch) return fail("t2s_prefill: batch %d outside [1,%d]", B, e->cfg.max_batch);
-  if (P < 0) return fail("t2s_prefill: negative prompt_len");
-  if (P > 0 && !rq->prompt) return fail("t2s_prefill: prompt_len > 0 but prompt is NULL");
-  if (rq->top_k < 1) return fail("t2s_prefill: top_k must be >= 1 (the reference's torch.topk fails otherwise)");
-  if (rq->max_steps < 1) return fail("t2s_prefill: max_steps must be >= 1");
-  if (!(rq->repetition_penalty > 0.f)) return fail("t2s_prefill: repetition_penalty must be > 0");
-  if (rq->bert_dtype < 0 || rq->bert_dtype > 2) return fail("t2s_prefill: bad bert_dtype");
+  if (B < 1 || B > e->cfg.max_batch) return fail("%s: batch %d outside [1,%d]", who, B, e->cfg.max_batch);
+  if (P < 0) return fail("%s: negative prompt_len", who);
+  if (P > 0 && !rq->prompt) return fail("%s: prompt_len > 0 but prompt is NULL", who);
+  if (rq->top_k < 1) return fail("%s: top_k must be >= 1 (the reference's torch.topk fails otherwise)", who);
+  if (rq->max_steps < 1) return fail("%s: max_steps must be >= 1", who);
+  if (!(rq->repetition_penalty > 0.f)) return fail("%s: repetition_penalty must be > 0", who);
+  if (rq->bert_dtype < 0 || rq->bert_dtype > 2) return fail("%s: bad bert_dtype", who);
   if (!rq->phoneme_ids || !rq->phoneme_lens || !rq->bert || !rq->bert_stride_c || !rq->bert_stride_t)
-    return fail("t2s_prefill: null input pointer");
+    return fail("%s: null input pointer", who);
   // early_stop_num: -1 = off; any other value n stops once more than n tokens were sampled (t2s_model.py:747/:897:
   // `early_stop_num != -1 and (len - prefix) > early_stop_num`), so n < -1 behaves like 0: stop at the first step
   const int early_stop = rq->early_stop_num == -1 ? -1 : std::max(rq->early_stop_num, 0);
   int steps_cap = rq->max_steps;
   if (early_stop >= 0) steps_cap = std::min(steps_cap, early_stop + 1);
+  int slot0 = 0, step0 = 0;
+  if (admit) {
+    if (!e->session) return fail("t2s_admit: no resident session (call t2s_prefill first)");
+    if (e->forced || e->logits_rec) {
+      // the per-step hooks are indexed [step][slot capacity]: fine, they were sized by the caller for the capacity
+    }
+    const Ctx& d = e->cd;
+    if (rq->top_k != d.top_k || rq->top_p != d.top_p || rq->temperature != d.temperature || rq->repetition_penalty != d.rep_pen ||
+        early_stop != d.early_stop || rq->eos_suppress_steps != d.eos_window || rq->max_steps != d.max_steps)
+      return fail("t2s_admit: sampling parameters / stop rules are per session and must equal those of t2s_prefill");
+    slot0 = e->B;
+    if (slot0 + B > e->cap) return fail("t2s_admit: %d more utterances do not fit the session's %d slots (%d in use; reserve them with "
+                                        "T2S_OPT_SESSION_SLOTS before t2s_prefill)", B, e->cap, slot0);
+    int n_active = 0, aborted = 0;
+    if (read_state(e, s, &n_active, &step0, &aborted)) return 1;
+    if (aborted) return fail("t2s_admit: the session is in an error state");
+    // the running sequences have completed global step step0 - 1 (their next sample is step0): the new ones' step 0 is sampled
+    // now AS step step0 - 1, so that old and new sequences take the session's next step together
+    step0 -= 1;
+    if (step0 < 0) return fail("t2s_admit: the session has not completed its first step");
+    if (n_active + B > e->max_clusters * cs::RMAX)
+      return fail("t2s_admit: %d active + %d new sequences exceed the %d the cluster-stream decode kernel holds", n_active, B, e->max_clusters * cs::RMAX);
+  }
   std::vector<int> text_len(B), text_off(B), s0(B), row0(B);
-  int n_text = 0, T = 0, max_pages = 0;
+  int n_text = 0, T = 0, need_pages = 0;
   for (int b = 0; b < B; ++b) {
     const int L = rq->phoneme_lens[b];
-    if (L < 1) return fail("t2s_prefill: utterance %d has %d phonemes", b, L);
+    if (L < 1) return fail("%s: utterance %d has %d phonemes", who, b, L);
     text_len[b] = L; text_off[b] = n_text; n_text += L;
     s0[b] = L + P; row0[b] = T; T += L + P;
     if (std::max(L, P + steps_cap) >= e->cfg.pe_len)
-      return fail("t2s_prefill: position %d exceeds the %d-entry positional table (embedding.py:52)", std::max(L, P + steps_cap), e->cfg.pe_len);
-    max_pages = std::max(max_pages, (s0[b] + steps_cap + PAGE - 1) / PAGE);
+      return fail("%s: position %d exceeds the %d-entry positional table (embedding.py:52)", who, std::max(L, P + steps_cap), e->cfg.pe_len);
+    need_pages = std::max(need_pages, (s0[b] + steps_cap + PAGE - 1) / PAGE);
   }
-  // ---- KV pool + page table (pages handed out contiguously per slot)
-  std::vector<int> page_table((size_t)B * max_pages, 0);
-  size_t pages = 0;
+  // ---- session geometry: slot capacity and pages per slot are fixed by t2s_prefill
+  if (!admit) {
+    e->cap = std::min(e->cfg.max_batch, std::max(B, e->session_slots));
+    e->sess_max_pages = std::max(need_pages, (e->session_positions + PAGE - 1) / PAGE);
+    e->next_page = 0;
+    e->h_page_table.assign((size_t)e->cap * e->sess_max_pages, 0);
+  } else if (need_pages > e->sess_max_pages) {
+    return fail("t2s_admit: an utterance needs %d K/V pages, the session was opened with %d per slot (T2S_OPT_SESSION_POSITIONS)", need_pages, e->sess_max_pages);
+  }
+  const int max_pages = e->sess_max_pages, cap = e->cap;
+  // ---- KV pool + page table (pages handed out contiguously per slot).  A fresh session sizes the pool for its CAPACITY when slots
+  //      were reserved (the pool cannot grow under a resident session: its contents are the session), else for what it uses.
   for (int b = 0; b < B; ++b) {
     const int np = (s0[b] + steps_cap + PAGE - 1) / PAGE;
-    for (int i = 0; i < np; ++i) page_table[(size_t)b * max_pages + i] = (int)pages++;
+    for (int i = 0; i < np; ++i) e->h_page_table[(size_t)(slot0 + b) * max_pages + i] = (int)e->next_page++;
   }
-  if (pages > e->pool_pages) {
-    const size_t bytes = (size_t)e->cfg.n_layer * pages * KV_PAGE_STRIDE * 2;  // K and V interleaved per (page, head)
-    CK(cudaStreamSynchronize(s));
-    if (e->kpool.ensure(bytes)) return 1;
-    e->pool_pages = pages;
+  {
+    const size_t pages = admit ? e->next_page : std::max(e->next_page, (size_t)(cap > B ? (size_t)cap * max_pages : 0));
+    if (pages > e->pool_pages) {
+      if (admit) return fail("t2s_admit: K/V pool exhausted (%zu pages needed, %zu reserved)", pages, e->pool_pages);
+      const size_t bytes = (size_t)e->cfg.n_layer * pages * KV_PAGE_STRIDE * 2;  // K and V interleaved per (page, head)
+      CK(cudaStreamSynchronize(s));
+      if (e->kpool.ensure(bytes)) return 1;
+      e->pool_pages = pages;
+    }
   }
-  // ---- host-built index arrays
+  const std::vector<int>& page_table = e->h_page_table;
+  // ---- host-built index arrays of THIS request's prompt rows
   std::vector<int> row_slot(T), row_pos(T), head_rows(B), trow_slot(n_text), trow_j(n_text), trow_row(n_text);
   std::vector<QTile> qtiles;
   for (int b = 0, r = 0, tr = 0; b < B; ++b) {
     for (int j = 0; j < s0[b]; ++j, ++r) {
-      row_slot[r] = b; row_pos[r] = j;
+      row_slot[r] = slot0 + b; row_pos[r] = j;
       if (j < text_len[b]) { trow_slot[tr] = b; trow_j[tr] = j; trow_row[tr] = r; ++tr; }
     }
     head_rows[b] = r - 1;
-    for (int q0 = 0; q0 < s0[b]; q0 += 64) qtiles.push_back(QTile{b, q0, row0[b] + q0, std::min(64, s0[b] - q0)});
+    for (int q0 = 0; q0 < s0[b]; q0 += 64) qtiles.push_back(QTile{slot0 + b, q0, row0[b] + q0, std::min(64, s0[b] - q0)});
   }
   const size_t R = (size_t)std::max(T, MAX_B);
-  const size_t n_ints = (size_t)2 * R + B * 4 + (size_t)3 * n_text + page_table.size() + qtiles.size() * 4 + 64;
+  const size_t n_ints = (size_t)2 * R + B * 5 + (size_t)3 * n_text + qtiles.size() * 4 + 64;
   int rc = 0;
   rc |= e->ints.ensure(n_ints * 4);
-  rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
   rc |= e->kvoff.ensure(R * 8);
   rc |= e->x0_rows.ensure((size_t)T * D * 4);
   rc |= e->x0b_rows.ensure((size_t)T * D * 2);
@@ -550,10 +597,16 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   rc |= e->h.ensure(R * FF * 2);
   rc |= e->y2.ensure(R * D * 4);
   rc |= e->stat2.ensure(R * 8);
-  rc |= e->gen.ensure((size_t)B * rq->max_steps * 4);
-  rc |= e->sampled.ensure((size_t)B * rq->max_steps * 4);
   rc |= e->bert_rows.ensure((size_t)n_text * BERT * 2);
   if (e->prefill_gemm) { rc |= e->xf.ensure((size_t)T * D * 4); rc |= e->xb.ensure((size_t)T * D * 2); }
+  if (!admit) {  // session buffers (a resident session's must not move)
+    rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
+    rc |= e->gen.ensure((size_t)cap * rq->max_steps * 4);
+    rc |= e->sampled.ensure((size_t)cap * rq->max_steps * 4);
+    rc |= e->page_tab.ensure((size_t)cap * max_pages * 4);
+    rc |= e->drows.ensure((size_t)MAX_B * 16);
+    rc |= e->slot_prompt.ensure((size_t)MAX_B * 8);
+  }
   if (rc) return 1;
   // pack the int arrays into one upload
   std::vector<int> hi(n_ints, 0);
@@ -565,13 +618,17 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   const size_t o_toff = put(text_off.data(), B);
   const size_t o_tlen = put(text_len.data(), B);
   const size_t o_s0 = put(s0.data(), B);
+  std::vector<int> new_slots(B);
+  for (int b = 0; b < B; ++b) new_slots[b] = slot0 + b;
+  const size_t o_new = put(new_slots.data(), B);
   const size_t o_ts = put(trow_slot.data(), n_text);
   const size_t o_tj = put(trow_j.data(), n_text);
   const size_t o_tr = put(trow_row.data(), n_text);
-  const size_t o_pt = put(page_table.data(), page_table.size());
   o = (o + 3) & ~(size_t)3;
   const size_t o_qt = put(reinterpret_cast<const int*>(qtiles.data()), qtiles.size() * 4);
   CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->page_tab.as<int>() + (size_t)slot0 * max_pages, page_table.data() + (size_t)slot0 * max_pages,
+                     (size_t)B * max_pages * 4, cudaMemcpyHostToDevice, s));
   std::vector<long long> kvoff(T);
   for (int r = 0; r < T; ++r)
     kvoff[r] = kv_row_off(page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> PAGE_SHIFT)], row_pos[r] & (PAGE - 1));
@@ -579,7 +636,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   int* di = e->ints.as<int>();
   e->d_row_slot = di + o_row_slot; e->d_row_pos = di + o_row_pos; e->d_head_rows = di + o_head;
   e->d_text_off = di + o_toff; e->d_text_len = di + o_tlen; e->d_s0 = di + o_s0;
-  e->d_trow_slot = di + o_ts; e->d_trow_j = di + o_tj; e->d_trow_row = di + o_tr; e->d_page_table = di + o_pt;
+  e->d_trow_slot = di + o_ts; e->d_trow_j = di + o_tj; e->d_trow_row = di + o_tr; e->d_page_table = e->page_tab.as<int>();
   e->d_qtiles = reinterpret_cast<QTile*>(di + o_qt);
   e->n_qtiles = (int)qtiles.size();
   // ---- inputs: device pointers, or host buffers copied here (end-to-end form)
@@ -590,6 +647,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   std::vector<long long> bsc(B), bst(B);
   const size_t es = dtype_size(rq->bert_dtype);
   if (rq->inputs_on_host) {
+    if (admit) return fail("t2s_admit: host inputs are not supported (the session keeps pointers to the prompt rows)");
     if (e->in_ids.ensure((size_t)n_text * 8) || e->in_bert.ensure((size_t)n_text * BERT * es) ||
         e->in_prompt.ensure((size_t)std::max(1, B * P) * 8))
       return 1;
@@ -621,51 +679,78 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
   CK(cudaMemcpyAsync(e->in_bert_ptrs.as<char>() + (size_t)B * 8, bsc.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(e->in_bert_ptrs.as<char>() + (size_t)B * 16, bst.data(), (size_t)B * 8, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // host staging vectors go out of scope below; uploads are tiny
-  e->prompt_dev = d_prompt; e->prompt_stride = prompt_stride;
-  e->B = B; e->P = P; e->T = T; e->n_text = n_text; e->max_steps = rq->max_steps;
+  if (!admit) { e->P = P; e->max_steps = rq->max_steps; }
+  e->maxP = admit ? std::max(e->maxP, P) : P;
+  e->T = T; e->n_text = n_text;
   e->h_text_len = text_len; e->h_s0 = s0;
   // ---- contexts
-  Ctx c{};
-  c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
-  c.head_c1 = e->head_c.as<float>(); c.head_c0 = e->head_c.as<float>() + VPAD;
-  c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
-  c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
-  c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len; c.phoneme_vocab = e->cfg.phoneme_vocab;
-  c.kpool = e->kpool.as<bf16>(); c.vpool = c.kpool + KV_V_OFF;
-  c.kv_layer_stride = e->pool_pages * (size_t)KV_PAGE_STRIDE;
-  c.page_table = e->d_page_table; c.max_pages = max_pages;
   int* i2 = e->ints2.as<int>();
-  c.n_rows = i2 + 0; c.n_active = i2 + 1; c.step = i2 + 2; c.abort_flag = i2 + 3;
-  c.bar = reinterpret_cast<unsigned*>(i2 + 4);
-  c.stats = reinterpret_cast<unsigned long long*>(i2 + 8);  // 3 x u64, 8-byte aligned
-  c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
-  c.row_slot = e->d_row_slot; c.row_pos = e->d_row_pos; c.row_kvoff = e->kvoff.as<long long>();
+  Ctx c{};
+  if (admit) {
+    c = e->cd;  // the session's model pointers, sampling parameters, token buffers, counters
+  } else {
+    c.wmat = e->wmat.as<bf16>(); c.wvec = e->wvec.as<float>(); c.whead = e->whead.as<bf16>(); c.wbert = e->wbert.as<bf16>();
+    c.head_c1 = e->head_c.as<float>(); c.head_c0 = e->head_c.as<float>() + VPAD;
+    c.bbert = e->bbert.as<float>(); c.emb_audio = e->emb_audio.as<bf16>(); c.emb_text = e->emb_text.as<bf16>();
+    c.pe = e->pe.as<float>(); c.alpha_audio = e->alpha_audio; c.alpha_text = e->alpha_text;
+    c.n_layer = e->cfg.n_layer; c.pe_len = e->cfg.pe_len; c.phoneme_vocab = e->cfg.phoneme_vocab;
+    c.kpool = e->kpool.as<bf16>(); c.vpool = c.kpool + KV_V_OFF;
+    c.kv_layer_stride = e->pool_pages * (size_t)KV_PAGE_STRIDE;
+    c.page_table = e->d_page_table; c.max_pages = max_pages;
+    c.n_rows = i2 + 0; c.n_active = i2 + 1; c.step = i2 + 2; c.abort_flag = i2 + 3;
+    c.bar = reinterpret_cast<unsigned*>(i2 + 4);
+    c.stats = reinterpret_cast<unsigned long long*>(i2 + 8);  // 3 x u64, 8-byte aligned
+    c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
+    c.slot_step0 = i2 + 16 + 4 * MAX_B; c.slot_P = i2 + 16 + 5 * MAX_B;
+    c.slot_prompt = e->slot_prompt.as<const long long*>();
+    c.logits = e->logits.as<float>();
+    c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
+    c.attn_desc = e->attn_desc.as<int>();
+    c.attn_ctas = ((e->decode_mode == 1 || e->decode_mode == 5) && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
+    c.B0 = cap; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
+    c.early_stop = early_stop; c.top_k = rq->top_k;
+    c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
+    c.seed_lo = (uint32_t)(rq->seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(rq->seed >> 32);
+    c.slot_base = e->slot_base;
+    c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
+    c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
+    c.seen = e->seen.as<uint32_t>();
+    c.timeline = e->timeline; c.tl_step = e->tl_step; c.tl_slots = e->tl_slots;
+  }
+  c.P = P;  // this request's prompt length (k_init_session stores it per slot)
+  // activations of this call's rows (may have been re-allocated)
   c.q = e->q.as<float>(); c.attn = e->attn.as<bf16>(); c.y1 = e->y1.as<float>(); c.h = e->h.as<bf16>();
   c.yb1 = e->yb1.as<bf16>(); c.yb2 = e->yb2.as<bf16>(); c.sp1 = e->sp1.as<float2>(); c.sp2 = e->sp2.as<float2>();
-  c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>(); c.logits = e->logits.as<float>();
-  c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
-  c.attn_desc = e->attn_desc.as<int>();
-  c.attn_ctas = ((e->decode_mode == 1 || e->decode_mode == 5) && e->num_ctas > 0) ? std::min(e->num_ctas, e->num_sms) : e->num_sms;
-
-  c.B0 = B; c.P = P; c.max_steps = rq->max_steps; c.eos_window = rq->eos_suppress_steps;
-  c.early_stop = early_stop; c.top_k = rq->top_k;
-  c.top_p = rq->top_p; c.temperature = rq->temperature; c.rep_pen = rq->repetition_penalty;
-  c.seed_lo = (uint32_t)(rq->seed & 0xFFFFFFFFull); c.seed_hi = (uint32_t)(rq->seed >> 32);
-  c.slot_base = e->slot_base;
-  c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
-  c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
-  c.seen = e->seen.as<uint32_t>();
-  c.timeline = e->timeline; c.tl_step = e->tl_step; c.tl_slots = e->tl_slots;
-  e->cp = c; e->cp.x0 = e->x0_rows.as<float>(); e->cp.x0b = e->x0b_rows.as<bf16>(); e->cp.x0_by_slot = 0; e->cp.head_rows = e->d_head_rows;
-  e->cd = c; e->cd.x0 = e->x0_slots.as<float>(); e->cd.x0b = e->x0b_slots.as<bf16>(); e->cd.x0_by_slot = 1; e->cd.head_rows = nullptr;
+  c.y2 = e->y2.as<float>(); c.stat2 = e->stat2.as<float2>();
+  // decode context: rows of the ACTIVE sequences (own arrays: an admit's prefill must not disturb them)
+  Ctx cd = c;
+  cd.row_slot = e->drows.as<int>(); cd.row_pos = cd.row_slot + MAX_B; cd.row_kvoff = reinterpret_cast<long long*>(cd.row_slot + 2 * MAX_B);
+  cd.x0 = e->x0_slots.as<float>(); cd.x0b = e->x0b_slots.as<bf16>(); cd.x0_by_slot = 1; cd.head_rows = nullptr;
+  // prefill context: this request's prompt rows; with admit its "active list" is the list of new slots and its row count a scratch word
+  Ctx cpx = c;
+  cpx.row_slot = e->d_row_slot; cpx.row_pos = e->d_row_pos; cpx.row_kvoff = e->kvoff.as<long long>();
+  cpx.x0 = e->x0_rows.as<float>(); cpx.x0b = e->x0b_rows.as<bf16>(); cpx.x0_by_slot = 0; cpx.head_rows = e->d_head_rows;
+  Ctx cs0 = cd;  // step-0 sampler of the new utterances: logits row b <-> slot slot0 + b
+  if (admit) {
+    int* scratch = reinterpret_cast<int*>(e->misc.as<char>() + 192);  // [n_rows, n_active] of the admitted request
+    cpx.n_rows = scratch; cpx.n_active = scratch + 1;
+    cs0.n_rows = scratch; cs0.n_active = scratch + 1; cs0.active = di + o_new; cs0.step = scratch + 2;
+    const int three[3] = {T, B, step0};
+    CK(cudaMemcpyAsync(scratch, three, 12, cudaMemcpyHostToDevice, s));
+  }
+  e->cd = cd; e->cp = cpx;
   const Ctx& cp = e->cp;
   // ---- launch
   CK(cudaEventRecord(e->ev0, s));
   const int g = e->num_sms;
-  CK(cudaMemsetAsync(e->cd.abort_flag, 0, 4, s));
-  k_init_session<<<B, 128, 0, s>>>(e->cd, d_prompt, prompt_stride, e->d_s0);
-  CK(cudaMemcpyAsync(cp.n_rows, &e->T, 4, cudaMemcpyHostToDevice, s));
-  k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride);
+  if (!admit) CK(cudaMemsetAsync(cd.abort_flag, 0, 4, s));
+  Ctx ci = cd; ci.P = P;
+  k_init_session<<<B, 128, 0, s>>>(ci, d_prompt, prompt_stride, e->d_s0, slot0, step0, admit ? 0 : 1);
+  if (!admit) {
+    CK(cudaMemcpyAsync(cp.n_rows, &e->T, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(e->llbuf.p, 0, 64, s));  // wide decode: the tag sequence of the hand-off cells restarts (cells are compared for equality)
+  }
+  k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride, slot0);
   const void* const* dptr = reinterpret_cast<const void* const*>(e->in_bert_ptrs.p);
   const long long* dsc = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 8);
   const long long* dst_ = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 16);
@@ -677,6 +762,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
     k_bert_rows<bf16><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
   k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
   e->launches += 4;
+  const int* d_text_len_by_slot = e->d_text_len - slot0;  // the attention kernels index text_len by session slot
   if (e->prefill_gemm) {
     // tcgen05/TMEM + TMA GEMMs (gemm_tc.cuh); LayerNorm rows are materialised once per sub-layer
     float* xf = e->xf.as<float>();
@@ -700,7 +786,7 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
       ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
       ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
       ok = ok && launch_gemm_tc<128>(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
-      k_prefill_attn_tc<<<dim3(e->n_qtiles, NH), 128, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+      k_prefill_attn_tc<<<dim3(e->n_qtiles, NH), 128, 0, s>>>(cp, l, e->d_qtiles, d_text_len_by_slot);
       ep = TcEpilogue{};
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;
@@ -712,39 +798,62 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
       ok = ok && launch_gemm_tc<128>(cp.h, wr + OFF_W2, T, D, FF, ep, s);
       e->launches += 7;
     }
-    if (!ok) return fail("t2s_prefill: cuTensorMapEncodeTiled failed");
+    if (!ok) return fail("%s: cuTensorMapEncodeTiled failed", who);
     k_rows_stats<<<(B + 7) / 8, 256, 0, s>>>(cp.y2, e->d_head_rows, B, cp.yb2, cp.sp2);
     e->launches++;
   } else {
-  for (int l = 0; l < cp.n_layer; ++l) {
+    for (int l = 0; l < cp.n_layer; ++l) {
       launch_phase<PH_QKV>(e, cp, l, g, s);
-      k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, e->d_text_len);
+      k_prefill_attn<<<dim3(e->n_qtiles, NH), 64, 0, s>>>(cp, l, e->d_qtiles, d_text_len_by_slot);
       e->launches++;
       launch_phase<PH_OPROJ>(e, cp, l, g, s);
       launch_phase<PH_FFN1>(e, cp, l, g, s);
       launch_phase<PH_FFN2>(e, cp, l, g, s);
     }
-}
-  launch_phase<PH_HEAD>(e, cp, 0, g, s);           // rows = n_active = B, gathered through head_rows
-  launch_phase<PH_SAMPLE>(e, e->cd, 0, std::min(B, g), s);  // step 0 sample; writes the decode-side x0
-  launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);
+  }
+  launch_phase<PH_HEAD>(e, cp, 0, g, s);            // rows = the request's B utterances, gathered through head_rows
+  launch_phase<PH_SAMPLE>(e, cs0, 0, std::min(B, g), s);  // step 0 sample of the new utterances; writes the decode-side x0
+  if (admit) {
+    k_admit<<<1, 256, 0, s>>>(e->cd, slot0, B);
+    e->launches++;
+  } else {
+    launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);
+  }
   CK(cudaEventRecord(e->ev1, s));
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_pinned + 8, e->cd.abort_flag, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (e->h_pinned[8] == ABORT_BAD_ID)
-    return fail("t2s_prefill: index out of range: a phoneme id lies outside [0,%d) or a prompt / forced token outside [0,%d) "
-                "(the reference's nn.Embedding raises IndexError here)", e->cfg.phoneme_vocab, V);
+    return fail("%s: index out of range: a phoneme id lies outside [0,%d) or a prompt / forced token outside [0,%d) "
+                "(the reference's nn.Embedding raises IndexError here)", who, e->cfg.phoneme_vocab, V);
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-  e->st.prefill_ms = ms;
-  e->st.decode_ms = 0.0;
-  e->st.decode_steps = 0;
-  e->st.decode_kv_positions = 0;
-  e->st.decode_tokens = 0;
-  e->st.prefill_rows = T;
-  e->session = true;
+  if (admit) {
+    e->st.prefill_ms += ms;
+    e->st.prefill_rows += T;
+    e->B = slot0 + B;
+  } else {
+    e->st.prefill_ms = ms;
+    e->st.decode_ms = 0.0;
+    e->st.decode_steps = 0;
+    e->st.decode_kv_positions = 0;
+    e->st.decode_tokens = 0;
+    e->st.prefill_rows = T;
+    e->B = B;
+    e->session = true;
+  }
   return 0;
+}
+
+extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) {
+  if (!e || !rq) return fail("t2s_prefill: null argument");
+  e->session = false;
+  return prefill_impl(e, rq, (cudaStream_t)stream_, false);
+}
+
+extern "C" int t2s_admit(t2s_engine* e, const t2s_request* rq, void* stream_) {
+  if (!e || !rq) return fail("t2s_admit: null argument");
+  return prefill_impl(e, rq, (cudaStream_t)stream_, true);
 }
 
 // ---- decode ----------------------------------------------------------------------------------------------
@@ -767,20 +876,20 @@ extern "C" int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream_, i
   if (n_active > 0 && budget > 0) {
     int mode = e->decode_mode;
     if (mode == 5) {  // auto: the cluster-stream kernel whenever the batch fits its 16-CTA clusters, else the grid-wide phases
-      const bool fits = e->max_clusters >= 1 && e->B <= e->max_clusters * cs::RMAX && e->cd.max_pages <= 32;
+      const bool fits = e->max_clusters >= 1 && n_active <= e->max_clusters * cs::RMAX && e->cd.max_pages <= 32;
       mode = fits ? 4 : 1;
     }
     if (mode == 1 && e->tc_ok && e->tc_decode_min_batch > 0 && e->B >= e->tc_decode_min_batch) mode = 3;
     if (mode == 3 && !e->tc_ok) return fail("t2s_decode: tcgen05 decode needs the TMA descriptor entry point");
     if (mode == 6) {
       if (!e->wide_ok) return fail("t2s_decode: wide decode unavailable (needs %d co-resident CTAs with %zu bytes of shared memory)", ws::G, sizeof(ws::Smem));
-      if (e->B > ws::RW) return fail("t2s_decode: wide decode holds at most %d sequences (got %d)", ws::RW, e->B);
+      if (n_active > ws::RW) return fail("t2s_decode: wide decode holds at most %d sequences (got %d)", ws::RW, n_active);
       if (e->cd.max_pages > 32) return fail("t2s_decode: wide decode supports at most 32 KV pages per sequence");
       if (e->cfg.n_layer + 1 >= (int)ws::TAG_STRIDE) return fail("t2s_decode: wide decode supports at most %d layers", (int)ws::TAG_STRIDE - 2);
     }
     if (mode == 4) {
       if (e->max_clusters < 1) return fail("t2s_decode: cluster-stream decode unavailable (no co-resident 16-CTA cluster)");
-      if (e->B > e->max_clusters * cs::RMAX) return fail("t2s_decode: cluster-stream decode holds at most %d sequences (got %d)", e->max_clusters * cs::RMAX, e->B);
+      if (n_active > e->max_clusters * cs::RMAX) return fail("t2s_decode: cluster-stream decode holds at most %d sequences (got %d)", e->max_clusters * cs::RMAX, n_active);
       if (e->cd.max_pages > 32) return fail("t2s_decode: cluster-stream decode supports at most 32 KV pages per sequence");
     }
     e->st.decode_mode = mode;
@@ -885,7 +994,7 @@ extern "C" int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride
   if (!e || !tokens_out || !idx_out) return fail("t2s_result: null argument");
   if (!e->session) return fail("t2s_result: no session");
   cudaStream_t s = (cudaStream_t)stream_;
-  const int width = e->P + e->max_steps;
+  const int width = e->maxP + e->max_steps;
   if (row_stride < width) return fail("t2s_result: row_stride %lld < P + max_steps = %d", (long long)row_stride, width);
   if (e->out_idx.ensure((size_t)e->B * 4)) return 1;
   long long* dst = reinterpret_cast<long long*>(tokens_out);
@@ -895,7 +1004,7 @@ extern "C" int t2s_result(t2s_engine* e, int64_t* tokens_out, int64_t row_stride
     dst = e->out_tokens.as<long long>();
     stride = width;
   }
-  k_finalize<<<e->B, 256, 0, s>>>(e->cd, e->prompt_dev, e->prompt_stride, dst, stride, e->out_idx.as<int>());
+  k_finalize<<<e->B, 256, 0, s>>>(e->cd, dst, stride, e->out_idx.as<int>());
   e->launches++;
   CK(cudaGetLastError());
   if (tokens_on_host)
@@ -1004,7 +1113,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
       const int t = prev ? prev[(size_t)r * m + j] : -1;
       if (t >= 0 && t < V) seen[(size_t)r * SEEN_WORDS + (t >> 5)] |= 1u << (t & 31);
     }
-  std::vector<int> i2(16 + 4 * MAX_B, 0);
+  std::vector<int> i2(16 + 6 * MAX_B, 0);  // ... + slot_step0 (0) + slot_P (0)
   i2[0] = n; i2[1] = n; i2[2] = step;
   for (int r = 0; r < n; ++r) i2[16 + MAX_B + r] = r;  // active = identity
   CK(cudaMemcpyAsync(e->logits.p, lg.data(), lg.size() * 4, cudaMemcpyHostToDevice, s));
@@ -1014,6 +1123,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   int* d2 = e->ints2.as<int>();
   c.n_rows = d2; c.n_active = d2 + 1; c.step = d2 + 2; c.abort_flag = d2 + 3;
   c.seq_len = d2 + 16; c.active = d2 + 16 + MAX_B; c.done = d2 + 16 + 2 * MAX_B; c.out_idx = d2 + 16 + 3 * MAX_B;
+  c.slot_step0 = d2 + 16 + 4 * MAX_B; c.slot_P = d2 + 16 + 5 * MAX_B;
   c.logits = e->logits.as<float>(); c.seen = e->seen.as<uint32_t>();
   c.gen = e->gen.as<int>(); c.sampled = c.gen + (size_t)n * ms; c.greedy_rec = c.gen + (size_t)2 * n * ms;
   c.B0 = n; c.P = 0; c.max_steps = ms; c.eos_window = (width == V) ? 0 : step + 1; c.early_stop = -1; c.top_k = top_k;

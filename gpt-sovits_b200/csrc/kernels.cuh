@@ -93,10 +93,13 @@ __global__ void __launch_bounds__(NT, 1) k_barrier_bench(unsigned* counter, int*
 }
 
 // ---- session initialisation ----------------------------------------------------------------------------
-// One CTA per slot: seen-bitmap from the prompt (previous_tokens = y includes the prompt,
-// t2s_model.py:714), counters, identity active list.
-__global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_row_stride, const int* s0) {
-  const int b = blockIdx.x, tid = threadIdx.x;
+// One CTA per utterance of the request: local index b = blockIdx.x, session slot = slot0 + b.  seen-bitmap from the prompt
+// (previous_tokens = y includes the prompt, t2s_model.py:714), per-slot counters.  fresh = 1: a new session (global counters
+// reset, identity active list); fresh = 0: t2s_admit adds the utterances to the resident session at global step `step0`
+// (k_admit appends them to the active list after their prefill).
+__global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_row_stride, const int* s0, int slot0, int step0,
+                               int fresh) {
+  const int b = blockIdx.x, tid = threadIdx.x, slot = slot0 + b;
   __shared__ unsigned bits[SEEN_WORDS];
   if (tid < SEEN_WORDS) bits[tid] = 0u;
   __syncthreads();
@@ -106,18 +109,63 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
     else atomicExch(c.abort_flag, ABORT_BAD_ID);  // nn.Embedding(1025) raises IndexError here (t2s_model.py:636)
   }
   __syncthreads();
-  if (tid < SEEN_WORDS) c.seen[(size_t)b * SEEN_WORDS + tid] = bits[tid];
+  if (tid < SEEN_WORDS) c.seen[(size_t)slot * SEEN_WORDS + tid] = bits[tid];
   if (tid == 0) {
-    c.done[b] = 0;
-    c.out_idx[b] = -1;
-    c.seq_len[b] = s0[b];
-    c.active[b] = b;
-    c.seg_cnt[b] = 0;
-    if (b == 0) {
-      *c.n_active = c.B0;
-      *c.step = 0;
-      c.stats[0] = c.stats[1] = c.stats[2] = 0ull;
+    c.done[slot] = 0;
+    c.out_idx[slot] = -1;
+    c.seq_len[slot] = s0[b];
+    c.slot_step0[slot] = step0;
+    c.slot_P[slot] = c.P;
+    const_cast<const long long**>(c.slot_prompt)[slot] = prompt + (long long)b * prompt_row_stride;
+    c.seg_cnt[slot] = 0;
+    if (fresh) {
+      c.active[slot] = slot;
+      if (b == 0) {
+        *c.n_active = gridDim.x;
+        *c.step = 0;
+        c.stats[0] = c.stats[1] = c.stats[2] = 0ull;
+      }
     }
+  }
+}
+
+// t2s_admit, after the new utterances' prefill and step-0 sample: append those that did not stop at once to the active list
+// and give them the row descriptors phase_plan would have produced (their first decode step is the session's next step).
+// One CTA; n_new <= MAX_B.
+__global__ void k_admit(Ctx c, int slot0, int n_new) {
+  __shared__ int keep_s[MAX_B];
+  __shared__ int base_s;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_new; i += blockDim.x) keep_s[i] = ld_cg_i(c.done + slot0 + i) ? 0 : 1;
+  __syncthreads();
+  if (tid == 0) {
+    const int n_old = ld_cg_i(c.n_active);
+    int p = n_old;
+    unsigned long long kv = 0;
+    for (int i = 0; i < n_new; ++i) {
+      if (!keep_s[i]) { keep_s[i] = -1; continue; }
+      keep_s[i] = p++;
+    }
+    base_s = p - n_old;
+    *c.n_active = p;
+    *c.n_rows = p;
+    (void)kv;
+    if (p > n_old) {
+      if (n_old == 0) atomicAdd(c.stats + 1, 1ull);  // the previous plan had scheduled no step: this one is scheduled now
+      atomicAdd(c.stats + 2, (unsigned long long)(p - n_old));
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_new; i += blockDim.x) {
+    const int p = keep_s[i];
+    if (p < 0) continue;
+    const int slot = slot0 + i, pos = ld_cg_i(c.seq_len + slot);
+    c.active[p] = slot;
+    c.row_slot[p] = slot;
+    c.row_pos[p] = pos;
+    c.row_kvoff[p] = kv_row_off(c.page_table[slot * c.max_pages + (pos >> PAGE_SHIFT)], pos & (PAGE - 1));
+    c.seq_len[slot] = pos + 1;
+    atomicAdd(c.stats + 0, (unsigned long long)(pos + 1));
   }
 }
 
@@ -125,10 +173,10 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
 // Row r = (slot, j).  Text rows:  emb_text[ph] + bert_proj.bias + alpha_t*pe[j]   (+ bert_proj GEMM, added
 // afterwards by the OUT_BERT projection phase);  audio rows: emb_audio[tok] + alpha_a*pe[j - L].
 __global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, const int* text_off,
-                             const int* text_len, const long long* prompt, long long prompt_row_stride) {
+                             const int* text_len, const long long* prompt, long long prompt_row_stride, int slot0) {
   const int r = blockIdx.x;
   if (r >= n_rows) return;
-  const int slot = c.row_slot[r], j = c.row_pos[r], L = text_len[slot];
+  const int slot = c.row_slot[r] - slot0, j = c.row_pos[r], L = text_len[slot];  // request-local utterance index
   float* out = c.x0 + (size_t)r * D;
   if (j < L) {
     long long ph = phoneme_ids[text_off[slot] + j];
@@ -447,15 +495,16 @@ __global__ void k_codes_to_latent(const long long* __restrict__ codes, int T, co
 }
 
 // ---- results: prompt ++ kept tokens, original batch order (t2s_model.py:733,753,779) -----------------
-__global__ void k_finalize(Ctx c, const long long* prompt, long long prompt_row_stride, long long* out,
-                           long long row_stride, int* idx_out) {
+__global__ void k_finalize(Ctx c, long long* out, long long row_stride, int* idx_out) {
   const int b = blockIdx.x;
   const int idx = c.out_idx[b];
   const int n = idx < 0 ? 0 : idx;
+  const int P = c.slot_P[b];
+  const long long* prompt = c.slot_prompt[b];
   long long* o = out + (long long)b * row_stride;
-  for (int i = threadIdx.x; i < c.P; i += blockDim.x) o[i] = prompt[(long long)b * prompt_row_stride + i];
-  for (int i = threadIdx.x; i < c.max_steps; i += blockDim.x)
-    o[c.P + i] = (i < n) ? (long long)c.gen[(size_t)b * c.max_steps + i] : -1ll;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) o[i] = prompt[i];
+  for (long long i = threadIdx.x; P + i < row_stride; i += blockDim.x)
+    o[P + i] = (i < n) ? (long long)c.gen[(size_t)b * c.max_steps + i] : -1ll;
   if (threadIdx.x == 0) idx_out[b] = idx;
 }
 

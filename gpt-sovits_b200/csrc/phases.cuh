@@ -799,24 +799,32 @@ __device__ void block_top_p(float (&x)[SV], const bool (&valid)[SV], int width, 
 }
 
 template <int SB>
-// slot_hint >= 0: the caller already knows the row's slot (saves a dependent global load in front of everything else)
-__device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm, int slot_hint = -1) {  // returns: the sequence stopped at this step
+// slot_hint >= 0: the caller already knows the row's slot (saves a dependent global load in front of everything else).
+// `gstep` is the session's GLOBAL step; the sequence's own step (the reference's idx) is gstep - slot_step0[slot]: utterances
+// admitted into a resident session (t2s_admit) start later than the first request's.
+__device__ bool sample_row(const Ctx& c, int r, int gstep, SampSmem& sm, int slot_hint = -1) {  // returns: the sequence stopped at this step
   const int tid = threadIdx.x;
-  const int width = (step < c.eos_window) ? (V - 1) : V;
   {
     const int slot = slot_hint >= 0 ? slot_hint : ld_cg_i(c.active + r);
     float v[SV];
     bool valid[SV];
     uint32_t sw[SV];  // the "seen" words of the repetition penalty: requested together with the logits (one L2 round trip)
     const uint32_t* seen = c.seen + (size_t)slot * SEEN_WORDS;
+    const int step0 = ld_cg_i(c.slot_step0 + slot), P = ld_cg_i(c.slot_P + slot);  // in flight with the logits
 #pragma unroll
     for (int j = 0; j < SV; ++j) {
       const int i = tid + NT * j;
-      valid[j] = i < width;
+      valid[j] = i < V;
       v[j] = valid[j] ? ld_cg_f(c.logits + (size_t)r * VPAD + i) : -INFINITY;
       sw[j] = (valid[j] && c.rep_pen != 1.0f) ? __ldcg(seen + (i >> 5)) : 0u;
-      if (c.logits_rec && step < c.n_logits_rec && i < V)
-        c.logits_rec[((size_t)step * c.B0 + slot) * V + i] = ld_cg_f(c.logits + (size_t)r * VPAD + i);
+    }
+    const int step = gstep - step0;
+    const int width = (step < c.eos_window) ? (V - 1) : V;
+#pragma unroll
+    for (int j = 0; j < SV; ++j) {
+      const int i = tid + NT * j;
+      if (c.logits_rec && step < c.n_logits_rec && i < V) c.logits_rec[((size_t)step * c.B0 + slot) * V + i] = v[j];
+      if (i >= width) { valid[j] = false; v[j] = -INFINITY; }
     }
     // repetition penalty over every distinct previous token (prompt + generated), utils.py:159-167
     if (c.rep_pen != 1.0f) {
@@ -899,7 +907,7 @@ __device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm, int slot
     if (!stop) {
       // next input: emb(y[:, -1]) * x_scale(=1) + alpha * pe[P + idx]  (t2s_model.py:766-769)
       const bf16* er = c.emb_audio + (size_t)emit * D;
-      const float* pr = c.pe + (size_t)min(c.P + step, c.pe_len - 1) * D;
+      const float* pr = c.pe + (size_t)min(P + step, c.pe_len - 1) * D;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int d = tid + NT * k;
@@ -914,7 +922,7 @@ __device__ bool sample_row(const Ctx& c, int r, int step, SampSmem& sm, int slot
 }
 
 __device__ void phase_sample(const Ctx& c, int n_active, int cta, int ncta, SampSmem& sm) {
-  const int step = ld_cg_i(c.step);
+  const int step = ld_cg_i(c.step);  // global step
   for (int r = cta; r < n_active; r += ncta) sample_row<0>(c, r, step, sm);
 }
 

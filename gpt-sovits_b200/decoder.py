@@ -122,6 +122,26 @@ def infer_panel(self, x, x_lens, prompts, bert_feature, top_k: int = -100, top_p
                              repetition_penalty, **kwargs)
 
 
+def infer_panel_stream(self, x: List[torch.LongTensor], x_lens: torch.LongTensor, prompts: torch.LongTensor,
+                       bert_feature: List[torch.Tensor], top_k: int = -100, top_p: int = 100, early_stop_num: int = -1,
+                       temperature: float = 1.0, repetition_penalty: float = 1.35, slice_steps: int = 25, **kwargs):
+    """Generator form of infer_panel_batch_infer for the reference's ``return_fragment`` mode (TTS.py:1049-1053, 1319-1329;
+    api_v2.py:348-365 streams the audio of each fragment as soon as it exists): yields ``(i, y_i, idx_i)`` - original batch
+    index, prompt ++ kept tokens, idx exactly as infer_panel_batch_infer returns them - in the order in which the sequences
+    RETIRE, while the rest of the batch keeps decoding, so SoVITS can start on the first finished sentence instead of waiting
+    for the slowest one.  Not part of the class-level patch (the reference has no such method); a caller opts in."""
+    from .batching import StreamingSession
+    if prompts is None:
+        raise RuntimeError("infer_panel_stream needs prompts (the reference's batched path has no reference-free mode)")
+    _check_top_k(top_k)
+    eng = engine_for(self)
+    sess = StreamingSession(eng, slots=len(x), slice_steps=slice_steps, top_k=top_k, top_p=top_p, temperature=temperature,
+                            repetition_penalty=repetition_penalty, early_stop_num=early_stop_num,
+                            eos_suppress_steps=EOS_WINDOW_BATCH, max_steps=MAX_STEPS)
+    sess.submit(list(x), list(bert_feature), prompts)
+    yield from sess
+
+
 _PATCHED: Dict[type, Dict[str, object]] = {}
 _METHODS = {"infer_panel": infer_panel, "infer_panel_naive": infer_panel_naive,
             "infer_panel_naive_batched": infer_panel_naive_batched, "infer_panel_batch_infer": infer_panel_batch_infer}

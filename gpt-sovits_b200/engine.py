@@ -54,10 +54,12 @@ class InferResult:
     logits: Optional[torch.Tensor] = None  # [n, B, 1025] raw logits of the first n steps (capture hook)
     sampled: Optional[torch.Tensor] = None  # [B, n] raw sampled tokens before teacher forcing
     stats: Dict[str, float] = field(default_factory=dict)
+    prompt_lens: Optional[List[int]] = None  # per slot, when utterances with other prompts were admitted into the session
 
     def sequences(self) -> List[torch.Tensor]:
         """prompt ++ kept tokens per utterance, original order (t2s_model.py:733,779)."""
-        return [self.tokens[b, : self.prompt_len + max(i, 0)] for b, i in enumerate(self.idx)]
+        P = self.prompt_lens or [self.prompt_len] * len(self.idx)
+        return [self.tokens[b, : P[b] + max(i, 0)] for b, i in enumerate(self.idx)]
 
 
 class T2SEngine:
@@ -135,28 +137,10 @@ class T2SEngine:
     def set_option(self, opt: int, value: int) -> None:
         _lib.check(self.lib.t2s_set_option(self._h, opt, int(value)))
 
-    # ---- one infer_panel call ------------------------------------------------------------------------
-    def infer(
-        self,
-        phoneme_ids: Sequence[torch.Tensor],
-        bert: Sequence[torch.Tensor],
-        prompt: Optional[torch.Tensor],
-        top_k: int = 15,
-        top_p: float = 1.0,
-        temperature: float = 1.0,
-        repetition_penalty: float = 1.35,
-        early_stop_num: int = -1,
-        eos_suppress_steps: int = EOS_WINDOW_BATCH,
-        max_steps: int = MAX_STEPS,
-        seed: Optional[int] = None,
-        forced: Optional[torch.Tensor] = None,
-        capture_logits: int = 0,
-        max_new_steps: int = -1,
-        host_io: bool = False,
-    ) -> InferResult:
-        """phoneme_ids: B tensors [L_i] int64; bert: B tensors [1024, L_i]; prompt: [B, P] int64 or None.
-        host_io=True takes CPU tensors and returns CPU tokens: the H2D / D2H copies happen inside the
-        C-ABI call (bench.py's end-to-end leg)."""
+    def _request(self, phoneme_ids, bert, prompt, top_k, top_p, temperature, repetition_penalty, early_stop_num,
+                 eos_suppress_steps, max_steps, seed, host_io):
+        """Validates one infer_panel-shaped call and packs it into the C-ABI request (include/t2s_b200.h t2s_request).
+        Returns (request, tensors to keep alive, batch, prompt length)."""
         B = len(phoneme_ids)
         if B == 0:
             raise ValueError("empty batch")
@@ -207,6 +191,45 @@ class T2SEngine:
             repetition_penalty=float(repetition_penalty), early_stop_num=int(early_stop_num),
             eos_suppress_steps=int(eos_suppress_steps), max_steps=int(max_steps), seed=int(seed) & (2 ** 64 - 1),
             inputs_on_host=1 if host_io else 0)
+        rq._keep = (lens_c, ptrs, sc, st)
+        return rq, (ids, bert, prompt), B, P
+
+    # ---- one infer_panel call ------------------------------------------------------------------------
+    def infer(
+        self,
+        phoneme_ids: Sequence[torch.Tensor],
+        bert: Sequence[torch.Tensor],
+        prompt: Optional[torch.Tensor],
+        top_k: int = 15,
+        top_p: float = 1.0,
+        temperature: float = 1.0,
+        repetition_penalty: float = 1.35,
+        early_stop_num: int = -1,
+        eos_suppress_steps: int = EOS_WINDOW_BATCH,
+        max_steps: int = MAX_STEPS,
+        seed: Optional[int] = None,
+        forced: Optional[torch.Tensor] = None,
+        capture_logits: int = 0,
+        max_new_steps: int = -1,
+        host_io: bool = False,
+        reserve_slots: int = 0,
+        reserve_positions: int = 0,
+    ) -> InferResult:
+        """phoneme_ids: B tensors [L_i] int64; bert: B tensors [1024, L_i]; prompt: [B, P] int64 or None.
+        host_io=True takes CPU tensors and returns CPU tokens: the H2D / D2H copies happen inside the
+        C-ABI call (bench.py's end-to-end leg).  reserve_slots / reserve_positions > 0 open the session with room for
+        later ``admit()`` calls (continuous batching): that many slots in total, that many K/V positions per slot."""
+        rq, keep, B, P = self._request(phoneme_ids, bert, prompt, top_k, top_p, temperature, repetition_penalty, early_stop_num,
+                                       eos_suppress_steps, max_steps, seed, host_io)
+        ids, bert, prompt = keep
+        dev = self.device
+        cap = max(B, int(reserve_slots))
+        self.set_option(_lib.OPT_SESSION_SLOTS, int(reserve_slots))
+        self.set_option(_lib.OPT_SESSION_POSITIONS, int(reserve_positions))
+        self._slot_P = [P] * B
+        self._session_kw = dict(top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
+                                early_stop_num=early_stop_num, eos_suppress_steps=eos_suppress_steps, max_steps=max_steps, seed=seed)
+        self._max_steps = int(max_steps)
         width = P + int(max_steps)
         with torch.cuda.device(dev):
             stream = self._stream()
@@ -219,7 +242,7 @@ class T2SEngine:
                 self._h, C.c_void_p(forced_dev.data_ptr()) if forced_dev is not None else None, n_forced))
             logits_buf = None
             if capture_logits > 0:
-                logits_buf = torch.full((capture_logits, B, self.vocab), float("nan"), device=dev, dtype=torch.float32)
+                logits_buf = torch.full((capture_logits, cap, self.vocab), float("nan"), device=dev, dtype=torch.float32)
             _lib.check(self.lib.t2s_set_logits_capture(
                 self._h, C.c_void_p(logits_buf.data_ptr()) if logits_buf is not None else None, int(capture_logits)))
             self._keep = [ids, bert, prompt, forced_dev, logits_buf]
@@ -236,6 +259,7 @@ class T2SEngine:
                 n = C.c_int32(0)
                 _lib.check(self.lib.t2s_decode(self._h, int(max_new_steps), stream, C.byref(n)))
                 _lib.check(self.lib.t2s_result(self._h, C.c_void_p(tokens.data_ptr()), width, 1 if host_io else 0, idx, stream))
+            # (with reserved slots logits_buf is [n, capacity, V]: the rows of admitted slots fill in as they decode)
             res = InferResult(tokens=tokens, idx=[int(v) for v in idx], prompt_len=P, logits=logits_buf, stats=self.stats())
             if forced is not None or capture_logits > 0:
                 n_s = max(n_forced, capture_logits, 1)
@@ -243,6 +267,33 @@ class T2SEngine:
                 _lib.check(self.lib.t2s_get_sampled(self._h, C.c_void_p(samp.data_ptr()), n_s, stream))
                 res.sampled = samp
         return res
+
+    def admit(self, phoneme_ids: Sequence[torch.Tensor], bert: Sequence[torch.Tensor], prompt: Optional[torch.Tensor]) -> List[int]:
+        """Continuous batching: adds utterances to the resident session (opened by ``infer(..., max_new_steps=k,
+        reserve_slots=n)``) at its current step; returns their slot indices (= their rows in ``result()``).  Sampling parameters
+        and stop rules are the session's; the prompt may differ from the first request's (C ABI: t2s_admit)."""
+        kw = self._session_kw
+        rq, keep, B, P = self._request(phoneme_ids, bert, prompt, kw["top_k"], kw["top_p"], kw["temperature"],
+                                       kw["repetition_penalty"], kw["early_stop_num"], kw["eos_suppress_steps"], kw["max_steps"],
+                                       kw["seed"] if kw["seed"] is not None else 0, False)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.t2s_admit(self._h, C.byref(rq), self._stream()))
+        self._keep.append(keep)
+        first = len(self._slot_P)
+        self._slot_P += [P] * B
+        return list(range(first, first + B))
+
+    def session_result(self) -> InferResult:
+        """``result()`` for every slot of the resident session, admitted ones included."""
+        return self.result(len(self._slot_P), max(self._slot_P), self._max_steps, prompt_lens=list(self._slot_P))
+
+    def sampled(self, n_steps: int) -> torch.Tensor:
+        """The raw sampled tokens (before teacher forcing) of every slot of the resident session, [slots, n_steps] int32 on the
+        host, indexed by each sequence's OWN step."""
+        samp = torch.empty((len(self._slot_P), n_steps), dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.t2s_get_sampled(self._h, C.c_void_p(samp.data_ptr()), n_steps, self._stream()))
+        return samp
 
     def decode_more(self, max_new_steps: int = -1) -> int:
         """Continue the resident session (after ``infer(..., max_new_steps=k)``) for at most ``max_new_steps`` further
@@ -253,14 +304,14 @@ class T2SEngine:
             _lib.check(self.lib.t2s_decode(self._h, int(max_new_steps), self._stream(), C.byref(n)))
         return int(n.value)
 
-    def result(self, batch: int, prompt_len: int, max_steps: int = MAX_STEPS) -> InferResult:
+    def result(self, batch: int, prompt_len: int, max_steps: int = MAX_STEPS, prompt_lens: Optional[List[int]] = None) -> InferResult:
         """Tokens / idx of the resident session as they stand (idx = -1: still decoding)."""
         width = prompt_len + int(max_steps)
         idx = (C.c_int32 * batch)()
         with torch.cuda.device(self.device):
             tokens = torch.empty((batch, width), dtype=torch.int64, device=self.device)
             _lib.check(self.lib.t2s_result(self._h, C.c_void_p(tokens.data_ptr()), width, 0, idx, self._stream()))
-        return InferResult(tokens=tokens, idx=[int(v) for v in idx], prompt_len=prompt_len, stats=self.stats())
+        return InferResult(tokens=tokens, idx=[int(v) for v in idx], prompt_len=prompt_len, stats=self.stats(), prompt_lens=prompt_lens)
 
     def codes_to_latent(self, codes: torch.Tensor, codebook: torch.Tensor, upsample: int = 2) -> torch.Tensor:
         """``F.interpolate(quantizer.decode(codes), size=upsample*T, mode="nearest")`` of SynthesizerTrn.decode

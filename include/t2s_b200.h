@@ -105,6 +105,16 @@ typedef struct {
  * sampled token (idx 0).  Leaves the session resident in the engine. */
 int t2s_prefill(t2s_engine* e, const t2s_request* req, void* stream);
 
+/* Continuous batching (the reference has no counterpart: TTS.run hands whole batches to infer_panel,
+ * TTS.py:1215): adds the request's utterances to the RESIDENT session at its current step - their prompt rows are prefilled
+ * and their step 0 is sampled here, the following t2s_decode calls advance old and new sequences together, each with its own
+ * idx / EOS window / early stop / Philox stream (sequences never interact, so an admitted utterance gets exactly the tokens it
+ * would get in a request of its own).  Slots and K/V pages must have been reserved before t2s_prefill
+ * (T2S_OPT_SESSION_SLOTS, T2S_OPT_SESSION_POSITIONS); sampling parameters and stop rules are per session and must match;
+ * the prompt length may differ.  Device inputs only; the prompt rows must stay valid for the session.  New slots follow the
+ * existing ones in t2s_result's order. */
+int t2s_admit(t2s_engine* e, const t2s_request* req, void* stream);
+
 /* The decode loop (t2s_model.py:701-769 / :878-914) for at most max_new_steps further steps
  * (-1: until every sequence has stopped).  Synchronises `stream`.  steps_run = steps executed. */
 int t2s_decode(t2s_engine* e, int32_t max_new_steps, void* stream, int32_t* steps_run);
@@ -167,11 +177,18 @@ enum {
                                 0: one kernel per phase over all SMs, CUDA-graph replay; 1: the same phases in one
                                 persistent cooperative kernel with grid barriers; 2: plain stream launches (profiling aid);
                                 3: CUDA graph with the projections on tcgen05 tensor cores (large batches);
-                                mode 1 switches to 3 by itself when batch >= T2S_OPT_TC_DECODE_MIN_BATCH */
+                                mode 1 switches to 3 by itself when batch >= T2S_OPT_TC_DECODE_MIN_BATCH;
+                                6: "wide" small-batch kernel (<= 8 sequences): every layer spread over 144 SMs, weights
+                                   through a TMA shared-memory ring, hand-offs through L2 {value, tag} cells; parity-green
+                                   but measured slower than mode 4, so auto never picks it */
   T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */
   T2S_OPT_NUM_CTAS = 2,      /* persistent grid size (0 = one CTA per SM) */
   T2S_OPT_CHECK_STEPS = 3,   /* graph mode: host checks the active count every this many steps */
-  T2S_OPT_TC_DECODE_MIN_BATCH = 4 /* batch size from which decode projections run on tcgen05 (default 160, the measured crossover; 0: never) */
+  T2S_OPT_TC_DECODE_MIN_BATCH = 4, /* batch size from which decode projections run on tcgen05 (default 160, the measured crossover; 0: never) */
+  T2S_OPT_SESSION_SLOTS = 5,     /* continuous batching: slots (utterances) the NEXT t2s_prefill reserves for the session, >= its own
+                                    batch (0 = exactly its batch: no t2s_admit possible); the K/V pool is sized for all of them */
+  T2S_OPT_SESSION_POSITIONS = 6  /* K/V positions reserved per slot (0 = what the first request's longest utterance needs:
+                                    phonemes + prompt + step cap); an admitted utterance must fit */
 };
 int t2s_set_option(t2s_engine* e, int32_t option, int64_t value);
 

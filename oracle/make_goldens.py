@@ -282,7 +282,40 @@ def case_fp16w_b1():
     print("fp16w_b1: idx", idx)
 
 
-ROUND2 = ("long_b2", "long_b1", "naive_batched", "cfg2_b32", "fp16w_b1")
+def case_to_batch():
+    """TTS.to_batch / TTS.recovery_order (TTS_infer_pack/TTS.py:842-973) run from the reference's OWN source: TTS.py itself cannot
+    be imported here (librosa, peft, ffmpeg, ...), so the two method definitions are cut out of the file with `ast` and executed
+    as plain functions (they do not touch `self`).  Recorded: the batch index lists for seeded length sets."""
+    import ast
+    import json
+    src = open("/root/reference/GPT_SoVITS/TTS_infer_pack/TTS.py").read()
+    tree = ast.parse(src)
+    fns = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("to_batch", "recovery_order"):
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"torch": torch, "np": np, "List": list}
+            exec(compile(mod, "TTS.py", "exec"), ns)
+            fns[node.name] = ns[node.name]
+    rs = np.random.RandomState(21)
+    cases = []
+    for n, bs, thr, split in ((1, 5, 0.75, True), (7, 3, 0.75, True), (23, 5, 0.75, True), (120, 20, 0.75, True), (120, 32, 0.9, True),
+                              (40, 8, 0.5, True), (40, 8, 1.0, True), (17, 4, 0.75, False), (64, 200, 0.75, True), (30, 1, 0.75, True)):
+        lens = [int(v) for v in rs.randint(3, 140, size=n)]
+        if n == 40:
+            lens[:10] = [50] * 10  # ties: the sort must be stable
+        data = [{"norm_text": "x" * L, "phones": [1] * (L + 2), "bert_features": torch.zeros(1024, L + 2)} for L in lens]
+        batches, index_list = fns["to_batch"](None, data, prompt_data=None, batch_size=bs, threshold=thr, split_bucket=split)
+        assert [len(b["all_phones"]) for b in batches] == [len(i) for i in index_list]
+        rec = fns["recovery_order"](None, [[lens[i] for i in idxs] for idxs in index_list], index_list)
+        assert rec == lens
+        cases.append({"lengths": lens, "batch_size": bs, "threshold": thr, "split_bucket": split,
+                      "batch_index_list": [[int(i) for i in idxs] for idxs in index_list]})
+    json.dump(cases, open(os.path.join(GOLD, "to_batch.json"), "w"))
+    print("to_batch:", len(cases), "cases;", [len(c["batch_index_list"]) for c in cases], "batches")
+
+
+ROUND2 = ("long_b2", "long_b1", "naive_batched", "cfg2_b32", "fp16w_b1", "to_batch")
 
 
 def main():
@@ -311,6 +344,7 @@ def main():
     case_naive_batched()
     case_cfg2_b32(model)
     case_fp16w_b1()
+    case_to_batch()
 
 
 if __name__ == "__main__":

@@ -251,3 +251,144 @@ def test_fp16_checkpoint_weights(golden_dir, pe_table):
           f"argmax agree {agree}/{n}")
     assert max(errs) <= FP16_CKPT_TOL
     assert agree >= n - 3
+
+
+# ---- continuous batching (t2s_admit) and fragment return, against the ORACLE / the reference goldens --------------------------
+def test_continuous_batching_admit_vs_oracle(engine_eos, pe_table):
+    """Utterances admitted into a resident session at later steps (other prompt lengths included) get exactly what the oracle
+    computes for each utterance on its own: teacher-forced per-step logits within the tolerance, the same idx, the same
+    tokens; the sequences already running are not disturbed.  (Sequences never interact: t2s_model.py:583-779.)"""
+    from oracle.t2s_oracle import T2SOracle
+    sd = synthetic.make_state_dict(seed=3, eos_scale=1.4)
+    o = T2SOracle(sd, pe_table)
+    groups = [([40, 64, 52], 60, 31), ([33, 47], 45, 32), ([64, 21], 60, 33)]  # (phoneme lengths, prompt length, input seed)
+    stop, n_rec = 36, 37
+    utt, ref = [], []
+    for L, P, seed in groups:
+        ids, lens, prompt, bert = synthetic.make_inputs(len(L), L, P, seed=seed)
+        for b in range(len(L)):
+            out = o.generate([ids[b].numpy()], [bert[b].numpy()], prompt[b:b + 1].numpy(), top_k=1, early_stop_num=stop,
+                             eos_window=1, record_logits=True)
+            ref.append(out)
+        utt.append(([t.cuda() for t in ids], [t.cuda() for t in bert], prompt.cuda()))
+    cap = len(ref)
+    forced = torch.zeros((cap, n_rec), dtype=torch.int32)
+    for k, out in enumerate(ref):
+        g = out["generated"][0]
+        forced[k, : len(g)] = torch.tensor(g, dtype=torch.int32)  # includes the token of the stopping step (EOS where it stopped on EOS)
+    eng = engine_eos
+    r0 = eng.infer(*utt[0], top_k=1, early_stop_num=stop, eos_suppress_steps=1, forced=forced, capture_logits=n_rec,
+                   max_new_steps=5, reserve_slots=cap, reserve_positions=64 + 60 + stop + 2)
+    logits = r0.logits  # [n_rec, cap, V], filled in as the session runs
+    assert int(r0.stats["decode_mode"]) == 4
+    assert eng.decode_more(4) == 4
+    slots1 = eng.admit(*utt[1])
+    assert slots1 == [3, 4]
+    assert eng.decode_more(6) == 6
+    slots2 = eng.admit(*utt[2])
+    assert slots2 == [5, 6]
+    while any(i < 0 for i in eng.session_result().idx):
+        assert eng.decode_more(16) > 0
+    res = eng.session_result()
+    lg = logits.cpu().numpy()
+    worst = 0.0
+    for k, out in enumerate(ref):
+        assert res.idx[k] == out["idx"][0], (k, res.idx, [r["idx"][0] for r in ref])
+        np.testing.assert_array_equal(res.sequences()[k].cpu().numpy(), out["tokens"][0])
+        for s in range(out["idx"][0] + 1):
+            w = 1024 if s < 1 else 1025
+            assert not np.isnan(lg[s, k, :w]).any(), (k, s)
+            worst = max(worst, float(np.abs(lg[s, k, :w] - out["logits"][s][0, :w]).max()))
+    print(f"continuous batching: 7 utterances in 3 admissions, idx {res.idx}, max |dlogit| vs oracle = {worst:.4f}")
+    assert worst <= LOGIT_TOL
+    assert len(set(res.idx)) > 2
+    # capacity and parameter checks
+    with pytest.raises(RuntimeError, match="do not fit"):
+        eng.admit(*utt[1])
+
+
+def test_admitted_utterance_keeps_its_philox_stream(engine, golden_dir):
+    """Sampling (top_k=15): the tokens of an ADMITTED utterance are the fp32 replay of its own logits with the Philox stream of
+    (seed, its slot, its OWN step) - admission time does not leak into the random numbers."""
+    from oracle import sampler_oracle as so
+    g = _golden(golden_dir, "batch_b4")
+    ids, bert, prompt = _inputs(g)
+    n, seed = 20, 777
+    kw = dict(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=n - 1, eos_suppress_steps=1, seed=seed)
+    r = engine.infer(ids[:2], bert[:2], prompt[:2], capture_logits=n, max_new_steps=7, reserve_slots=4, **kw)
+    logits = r.logits
+    engine.admit(ids[2:], bert[2:], prompt[2:])
+    while any(i < 0 for i in engine.session_result().idx):
+        engine.decode_more(8)
+    res = engine.session_result()
+    samp = engine.sampled(n)
+    lg = logits.cpu().numpy()
+    bad = 0
+    for b in range(4):
+        hist = list(map(int, prompt[b].cpu().numpy()))
+        for s in range(res.idx[b] + 1):
+            w = 1024 if s < 1 else 1025
+            tok, _, _, margin = so.sample_row(lg[s, b, :w].copy(), hist, so.exp_noise(seed, b, s, w), 1.0, 15, 1.0, 1.35)
+            if margin > 1e-4:
+                bad += int(int(samp[b, s]) != tok)
+            hist.append(int(samp[b, s]))
+        np.testing.assert_array_equal(res.sequences()[b].cpu().numpy()[int(g["prompt_len"]):], samp[b, : res.idx[b]].numpy())
+    assert bad == 0
+    assert all(0 <= i <= n - 1 for i in res.idx)
+
+
+def test_fragment_stream_vs_reference_golden(golden_dir, pe_table):
+    """return_fragment-style streaming (TTS.py:1049-1053, 1319-1329): sequences are handed out as they retire, in retirement
+    order, each with the (y, idx) the REFERENCE produced (goldens retire_b6), while the others keep decoding."""
+    import gpt_sovits_b200 as gsb
+    from gpt_sovits_b200 import decoder
+    g = _golden(golden_dir, "retire_b6")
+    sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), eos_scale=float(g["eos_scale"]))
+    eng = gsb.T2SEngine(synthetic.S1V2_CONFIG, device="cuda:0")
+    try:
+        eng.load_state_dict(sd, pe=pe_table)
+        ids, bert, prompt = _inputs(g)
+        P = int(g["prompt_len"])
+        ref_idx = [int(v) for v in g["idx"]]
+        n = g["logits"].shape[0]
+        forced = torch.zeros((6, n), dtype=torch.int32)
+        for b in range(6):
+            y = g["y"][b]
+            y = y[y >= 0][P:]
+            forced[b, : len(y)] = torch.from_numpy(y).to(torch.int32)
+            forced[b, ref_idx[b]] = 1024  # greedy reference: it stopped because its argmax was EOS
+        sess = gsb.StreamingSession(eng, slots=6, slice_steps=4, top_k=1, early_stop_num=int(g["early_stop_num"]),
+                                    eos_suppress_steps=1, forced=forced)
+        keys = sess.submit(ids, bert, prompt)
+        assert keys == list(range(6))
+        order, steps_at_yield = [], []
+        for key, y, idx in sess:
+            order.append(key)
+            steps_at_yield.append(int(eng.stats()["decode_steps"]))
+            ref = g["y"][key]
+            assert idx == ref_idx[key]
+            np.testing.assert_array_equal(y.cpu().numpy(), ref[ref >= 0])
+        assert sorted(order) == list(range(6))
+        assert [ref_idx[k] for k in order] == sorted(ref_idx)           # retirement order
+        assert steps_at_yield[0] < steps_at_yield[-1]                     # the first fragment left before the last sequence finished
+        assert steps_at_yield[0] <= min(ref_idx) + 4
+        # the reference-shaped generator, free running: every (i, y, idx) is the reference's unless greedy left its trajectory at a near tie
+        orig = decoder.engine_for
+        decoder.engine_for = lambda m: eng
+        try:
+            got = list(decoder.infer_panel_stream(object(), ids, torch.tensor([int(v) for v in g["phoneme_lens"]]), prompt, bert,
+                                                  top_k=1, top_p=1.0, early_stop_num=int(g["early_stop_num"]), temperature=1.0,
+                                                  repetition_penalty=1.35, slice_steps=5))
+        finally:
+            decoder.engine_for = orig
+        assert sorted(i for i, _, _ in got) == list(range(6))
+        same = 0
+        for i, y, idx in got:
+            ref = g["y"][i]
+            ref = ref[ref >= 0]
+            assert y.dtype == torch.int64 and y.is_cuda and y.shape[0] == P + idx
+            same += int(idx == ref_idx[i] and np.array_equal(y.cpu().numpy(), ref))
+        print(f"infer_panel_stream free running: {same}/6 sequences identical to the reference (near-tie steps may diverge)")
+        assert same >= 3
+    finally:
+        eng.close()

@@ -263,3 +263,24 @@ def _small_sd(**kw):
 
 
 _ORIG_MAKE_SD = synthetic.make_state_dict
+
+
+def test_bucket_batches_matches_reference_to_batch(golden_dir):
+    """bucket_batches / recovery_order against batch index lists recorded from the reference's own TTS.to_batch
+    (oracle/make_goldens.py case_to_batch): same batches, same order inside each batch, ties and thresholds included."""
+    import json
+
+    import gpt_sovits_b200 as gsb
+    cases = json.load(open(os.path.join(golden_dir, "to_batch.json")))
+    assert len(cases) >= 10
+    for c in cases:
+        got = gsb.bucket_batches(c["lengths"], c["batch_size"], c["threshold"], c["split_bucket"])
+        assert got == c["batch_index_list"], c
+        assert sorted(i for b in got for i in b) == list(range(len(c["lengths"])))
+        back = gsb.recovery_order([[c["lengths"][i] for i in b] for b in got], got)
+        assert back == c["lengths"]
+    assert gsb.bucket_batches([], 4) == []
+    with pytest.raises(ValueError):
+        gsb.bucket_batches([1, 2], 0)
+    with pytest.raises(ValueError):
+        gsb.recovery_order([[1]], [[0, 1]])
