@@ -463,7 +463,7 @@ static bool launch_decode_step_tc(t2s_engine* e, const Ctx& c, cudaStream_t s) {
     ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
     ep.mode = EPI_D_O; ep.bias = vl + VO_BO; ep.src_f32 = l == 0 ? x0r : c.y2; ep.stat_in = l == 0 ? nullptr : c.stat2;
     ep.g = vp + VO_G2; ep.be = vp + VO_BE2; ep.out_f32 = c.y1; ep.out_b16 = c.yb1; ep.sp_out = c.sp1;
-    ok = ok && launch_gemm_tc<64>(c.attn, wr + OFF_WO, B0, D, D, ep, s);
+    ok = ok && launch_gemm_tc<32>(c.attn, wr + OFF_WO, B0, D, D, ep, s);  // 512 outputs: 32-wide tiles put 2 x 16 CTAs on the weights
     ep = TcEpilogue{};
     ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
     ep.mode = EPI_D_FFN1; ep.bias = vl + VO_C0_FFN1; ep.c1 = vl + VO_C1_FFN1; ep.sp_in = c.sp1; ep.out_b16 = c.h;
@@ -472,7 +472,7 @@ static bool launch_decode_step_tc(t2s_engine* e, const Ctx& c, cudaStream_t s) {
     ep.error_flag = c.abort_flag; ep.n_rows = c.n_rows;
     ep.mode = EPI_D_FFN2; ep.src_f32 = c.y1; ep.sp_res = c.sp1; ep.g = vl + VO_G1; ep.be = vl + VO_BE1; ep.b2 = vl + VO_B2;
     ep.out_f32 = c.y2; ep.out_b16 = c.yb2; ep.sp_out = c.sp2;
-    ok = ok && launch_gemm_tc<64>(c.h, wr + OFF_W2, B0, D, FF, ep, s);
+    ok = ok && launch_gemm_tc<32>(c.h, wr + OFF_W2, B0, D, FF, ep, s);
     e->launches += 4;
   }
   launch_phase<PH_HEAD>(e, c, 0, g, s);

@@ -26,8 +26,12 @@ namespace t2s {
 // MMAs - with K = 512 a tile's main loop is only 8 k-blocks, the prologue and the epilogue are most of a CTA's life
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 256;
 template <int BN> struct TcCfg {
-  static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;  // 32 KB (BN=128) / 24 KB (BN=64)
-  static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;  // 32 KB (BN=128) / 24 KB (BN=64) / 20 KB (BN=32)
+  // Prefill (BN = 128, thousands of rows: throughput): 3 stages so that two CTAs share an SM.  Large-batch decode (BN <= 64, M <= 256
+  // rows: a handful of CTAs streaming the weights once): the tiles are LATENCY bound - with 3 stages a CTA has 72 KB in flight and
+  // the 32 k-blocks of linear2 take 11 HBM round trips - so the ring takes all the shared memory of an SM (8-9 stages, one CTA per SM).
+  static constexpr int STAGES = BN >= 128 ? TC_STAGES : (BN == 64 ? 8 : 9);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 };
@@ -139,14 +143,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
   // 1024-byte alignment for the 128B-swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * CF::STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), done_bar = smem_u32(bars + 2 * TC_STAGES);
+  constexpr int NST = CF::STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * CF::STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NST), done_bar = smem_u32(bars + 2 * NST);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / TC_BK;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -162,8 +167,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
+        const int s = kb % NST;
+        const uint32_t ph = (kb / NST) & 1;
         if (!mbar_wait(empty0 + 8 * s, ph ^ 1, ep.error_flag)) break;
         const uint32_t sa = smem_u32(smem + s * CF::STAGE_BYTES), sb = sa + TC_BM * TC_BK * 2;
         mbar_expect_tx(full0 + 8 * s, CF::STAGE_BYTES);
@@ -174,8 +179,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
+        const int s = kb % NST;
+        const uint32_t ph = (kb / NST) & 1;
         if (!mbar_wait(full0 + 8 * s, ph, ep.error_flag)) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * CF::STAGE_BYTES), sb = sa + TC_BM * TC_BK * 2;
@@ -328,6 +333,7 @@ static inline bool gemm_tc_init() {
   g_tmap_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES);
   return true;
 }
 
