@@ -315,7 +315,28 @@ def case_to_batch():
     print("to_batch:", len(cases), "cases;", [len(c["batch_index_list"]) for c in cases], "batches")
 
 
-ROUND2 = ("long_b2", "long_b1", "naive_batched", "cfg2_b32", "fp16w_b1", "to_batch")
+S1_V1_MODEL = {"vocab_size": 1025, "phoneme_vocab_size": 512, "embedding_dim": 512, "hidden_dim": 512, "head": 16,
+               "linear_units": 2048, "n_layer": 12, "dropout": 0, "EOS": 1024}  # GPT_SoVITS/configs/s1.yaml (the v1 architecture)
+
+
+def case_ckpt_s1v1():
+    """The v1 s1 architecture (configs/s1.yaml: 12 layers, 512 phonemes) loaded the way TTS.init_t2s_weights loads a checkpoint
+    (fp16 tensors under "weight" with the Lightning "model." prefix, TTS.py:585-599): the reference model receives the fp16 values
+    (as fp32) and runs infer_panel_batch_infer; the GPU test writes the same checkpoint file and goes file -> engine."""
+    cfg = {"model": dict(S1_V1_MODEL)}
+    sd = synthetic.make_state_dict(seed=21, config=cfg, rounding="fp16")
+    model = ref_harness.build_reference_model(sd, cfg)
+    L = [31, 56, 44]
+    ids, lens, prompt, bert = synthetic.make_inputs(3, L, 72, seed=22, phoneme_vocab=512)
+    y, idx, hook = _run(model, "infer_panel_batch_infer", (ids, lens, prompt, bert),
+                        dict(top_k=1, top_p=1.0, temperature=1.0, early_stop_num=20, repetition_penalty=1.35, max_len=max(L)))
+    np.savez_compressed(os.path.join(GOLD, "ckpt_s1v1.npz"), weight_seed=21, rounding="fp16", input_seed=22, phoneme_lens=L,
+                        prompt_len=72, phoneme_vocab=512, n_layer=12, top_k=1, repetition_penalty=1.35, early_stop_num=20,
+                        logits=_pad_logits(hook.logits), y=np.stack([t.numpy() for t in y]), idx=np.array(idx))
+    print("ckpt_s1v1: idx", idx)
+
+
+ROUND2 = ("long_b2", "long_b1", "naive_batched", "cfg2_b32", "fp16w_b1", "to_batch", "ckpt_s1v1")
 
 
 def main():
@@ -345,6 +366,7 @@ def main():
     case_cfg2_b32(model)
     case_fp16w_b1()
     case_to_batch()
+    case_ckpt_s1v1()
 
 
 if __name__ == "__main__":

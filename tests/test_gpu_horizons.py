@@ -129,16 +129,24 @@ def test_long_context_b1_crossing_1500(engine, golden_dir, mode):
     np.testing.assert_array_equal(res.sequences()[0].cpu().numpy(), g["y"][0])
 
 
-@pytest.mark.parametrize("mode", [1, 4])
+@pytest.mark.parametrize("mode", [1, 4, 3])
 def test_cfg2_b32_logits(engine, golden_dir, mode):
-    """The bench configuration itself, against the reference: 16 steps teacher-forced with the tokens the reference sampled."""
+    """The bench configuration itself, against the reference: 16 steps teacher-forced with the tokens the reference sampled.
+    mode 3 = the large-batch path (decode projections on tcgen05 GEMMs, CUDA graph), forced on at this batch size: it, too, is
+    compared with the reference, not with another CUDA mode."""
+    from gpt_sovits_b200 import _lib
     g = _golden(golden_dir, "cfg2_b32")
-    _set_mode(engine, mode, 32)
+    if mode == 3:
+        engine.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, 32)
+        _set_mode(engine, 1, 32)
+    else:
+        _set_mode(engine, mode, 32)
     ids, bert, prompt = _inputs(g)
     n = g["logits"].shape[0]
     forced = torch.from_numpy(g["emitted"]).to(torch.int32)
     res = engine.infer(ids, bert, prompt, top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35,
                        early_stop_num=int(g["early_stop_num"]), eos_suppress_steps=1, forced=forced, capture_logits=n, seed=1)
+    engine.set_option(_lib.OPT_TC_DECODE_MIN_BATCH, 160)
     assert int(res.stats["decode_mode"]) == mode
     worst, agree, total = _worst(res, g, 1, [n] * 32)
     print(f"cfg2_b32 mode={mode}: max |dlogit| = {worst:.4f}, raw-argmax agree {agree}/{total}")
@@ -390,5 +398,42 @@ def test_fragment_stream_vs_reference_golden(golden_dir, pe_table):
             same += int(idx == ref_idx[i] and np.array_equal(y.cpu().numpy(), ref))
         print(f"infer_panel_stream free running: {same}/6 sequences identical to the reference (near-tie steps may diverge)")
         assert same >= 3
+    finally:
+        eng.close()
+
+
+def test_checkpoint_file_s1_v1_architecture_vs_reference(tmp_path, golden_dir, pe_table):
+    """Checkpoint wire format -> engine against the REFERENCE, on the other 512-d member of the s1 family:
+    configs/s1.yaml (12 layers, 512 phonemes).  The file is written as process_ckpt.py writes it (fp16 tensors, "model." prefix,
+    config, info); engine_from_checkpoint() reads, validates and packs it; the teacher-forced logits are compared with the
+    goldens the unmodified reference produced from the same fp16 values."""
+    import gpt_sovits_b200 as gsb
+    g = _golden(golden_dir, "ckpt_s1v1")
+    model_cfg = {"vocab_size": 1025, "phoneme_vocab_size": int(g["phoneme_vocab"]), "embedding_dim": 512, "hidden_dim": 512, "head": 16,
+                 "linear_units": 2048, "n_layer": int(g["n_layer"]), "dropout": 0, "EOS": 1024}
+    sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), config={"model": model_cfg}, rounding="fp16")
+    path = str(tmp_path / "s1-e8.ckpt")
+    torch.save({"weight": {"model." + k: v.half() for k, v in sd.items()}, "config": {"model": model_cfg, "data": {"max_sec": 54}},
+                "info": "GPT-e8"}, path)
+    eng, config = gsb.engine_from_checkpoint(path, pe=pe_table)
+    try:
+        assert config["data"]["max_sec"] == 54 and eng.n_layer == 12
+        L = [int(v) for v in g["phoneme_lens"]]
+        ids, lens, prompt, bert = synthetic.make_inputs(len(L), L, int(g["prompt_len"]), seed=int(g["input_seed"]), phoneme_vocab=512)
+        ids, bert, prompt = [t.cuda() for t in ids], [t.cuda() for t in bert], prompt.cuda()
+        P, n = int(g["prompt_len"]), g["logits"].shape[0]
+        forced = torch.from_numpy(g["y"][:, P:]).to(torch.int32)
+        res = eng.infer(ids, bert, prompt, top_k=1, early_stop_num=int(g["early_stop_num"]), eos_suppress_steps=1, forced=forced,
+                        capture_logits=n)
+        worst, agree, total = _worst(res, g, 1, [n] * len(L))
+        print(f"s1 v1 checkpoint file (12 layers, 512 phonemes, fp16): max |dlogit| vs reference = {worst:.4f}, greedy agree {agree}/{total}")
+        assert worst <= FP16_CKPT_TOL
+        assert agree >= total - 2
+        assert res.idx == [int(v) for v in g["idx"]]
+        # a phoneme id of the v2 symbol table (>= 512) is out of range for this checkpoint: an error, not a silent read
+        bad = [ids[0].clone(), ids[1], ids[2]]
+        bad[0][0] = 600
+        with pytest.raises(RuntimeError, match="out of range"):
+            eng.infer(bad, bert, prompt, top_k=1, early_stop_num=2)
     finally:
         eng.close()

@@ -165,6 +165,23 @@ def test_fp16_weights(golden_dir, pe_table):
     np.testing.assert_array_equal(out["tokens"][0], g["y"][0])
 
 
+def test_ckpt_s1_v1_architecture(golden_dir, pe_table):
+    """configs/s1.yaml (12 layers, 512 phonemes), fp16 checkpoint values: the other 512-d member of the s1 family."""
+    g = _load(golden_dir, "ckpt_s1v1")
+    cfg = {"model": dict(synthetic.S1V2_CONFIG["model"], n_layer=int(g["n_layer"]), phoneme_vocab_size=int(g["phoneme_vocab"]))}
+    sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), config=cfg, rounding="fp16")
+    L = [int(v) for v in g["phoneme_lens"]]
+    ids, lens, prompt, bert = synthetic.make_inputs(len(L), L, int(g["prompt_len"]), seed=int(g["input_seed"]), phoneme_vocab=512)
+    o = T2SOracle(sd, pe_table)
+    assert o.L == 12
+    out = o.generate([t.numpy() for t in ids], [t.numpy() for t in bert], prompt.numpy(), top_k=1,
+                     early_stop_num=int(g["early_stop_num"]), eos_window=EOS_WINDOW_BATCH, record_logits=True)
+    _check_logits(out, g, EOS_WINDOW_BATCH)
+    assert out["idx"] == [int(v) for v in g["idx"]]
+    for b in range(len(L)):
+        np.testing.assert_array_equal(out["tokens"][b], g["y"][b])
+
+
 def test_sampler_kat(golden_dir):
     g = _load(golden_dir, "sampler_kat")
     for i in range(g["logits"].shape[0]):
