@@ -362,7 +362,7 @@ def cfg3_strong(dev, rank, world, barrier):
         mine_count[0] = len(indices)
         r = eng.infer([ids[i] for i in indices], [bert[i] for i in indices], prompt[indices], top_k=c["top_k"], top_p=c["top_p"],
                       temperature=c["temperature"], repetition_penalty=c["repetition_penalty"], early_stop_num=c["cap"],
-                      eos_suppress_steps=c["eos_window"], max_steps=1500, seed=77)
+                      eos_suppress_steps=c["eos_window"], max_steps=1500, seed=77, utt_ids=list(indices))
         return r.sequences(), r.idx
 
     shard.sharded_infer(infer_fn, L, rank=rank, world=world)  # warm-up

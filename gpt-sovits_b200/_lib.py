@@ -26,7 +26,7 @@ F32, F16, BF16 = 0, 1, 2
 OPT_DECODE_MODE, OPT_PREFILL_GEMM, OPT_NUM_CTAS, OPT_CHECK_STEPS, OPT_TC_DECODE_MIN_BATCH = 0, 1, 2, 3, 4
 OPT_SESSION_SLOTS, OPT_SESSION_POSITIONS = 5, 6
 
-EXPORTS = ["t2s_create", "t2s_destroy", "t2s_last_error", "t2s_load_tensor", "t2s_prefill", "t2s_admit", "t2s_decode",
+EXPORTS = ["t2s_create", "t2s_destroy", "t2s_last_error", "t2s_load_tensor", "t2s_prefill", "t2s_admit", "t2s_release_slots", "t2s_set_utterance_ids", "t2s_decode",
            "t2s_result", "t2s_generate", "t2s_set_forced_tokens", "t2s_set_logits_capture",
            "t2s_get_sampled", "t2s_set_option", "t2s_get_stats", "t2s_sampler_test", "t2s_bench_barrier", "t2s_set_timeline",
            "t2s_codes_to_latent"]
@@ -110,6 +110,8 @@ def load() -> C.CDLL:
     lib.t2s_load_tensor.argtypes = [vp, i32, i32, vp, i32, i64, i32, vp]
     lib.t2s_prefill.argtypes = [vp, C.POINTER(Request), vp]
     lib.t2s_admit.argtypes = [vp, C.POINTER(Request), vp]
+    lib.t2s_release_slots.argtypes = [vp, C.POINTER(i32), i32, vp]
+    lib.t2s_set_utterance_ids.argtypes = [vp, C.POINTER(i32), i32]
     lib.t2s_decode.argtypes = [vp, i32, vp, C.POINTER(i32)]
     lib.t2s_result.argtypes = [vp, vp, i64, i32, C.POINTER(i32), vp]
     lib.t2s_generate.argtypes = [vp, C.POINTER(Request), vp, i64, i32, C.POINTER(i32), vp]

@@ -67,8 +67,10 @@ class StreamingSession:
         for key, tokens, idx in sess:           # tokens = prompt ++ kept tokens (int64, device), idx as the reference returns it
             ...
 
-    ``key`` is the position of the utterance in submission order.  Utterances never interact, so every utterance gets the tokens
-    it would get in a call of its own with the same seed (Philox streams are keyed by session slot)."""
+    ``key`` is the position of the utterance in submission order.  ``slots`` bounds the utterances decoding at the same time: a
+    finished utterance's slot (and K/V pages) is released when it is handed out and reused by the next admission, so one resident
+    session serves any number of utterances.  Utterances never interact and every Philox stream is keyed by (seed, key, own step),
+    so an utterance gets the same tokens whatever slot it lands in and whenever it is admitted."""
 
     def __init__(self, engine: T2SEngine, slots: int = 32, positions: int = 0, slice_steps: int = 25, top_k: int = 15,
                  top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, early_stop_num: int = -1,
@@ -81,8 +83,7 @@ class StreamingSession:
                        early_stop_num=early_stop_num, eos_suppress_steps=eos_suppress_steps, max_steps=max_steps, seed=seed)
         self.hooks = dict(forced=forced, capture_logits=capture_logits)
         self.waiting: List[Tuple[int, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = []  # (key, ids, bert, prompt row)
-        self.slot_key: List[int] = []      # session slot -> key
-        self.reported: List[bool] = []
+        self.slot_key: Dict[int, int] = {}  # session slot -> key of the utterance decoding in it
         self.n_submitted = 0
         self.started = False
         self.first_logits = None
@@ -111,44 +112,33 @@ class StreamingSession:
         return [w[0] for w in take], [w[1] for w in take], [w[2] for w in take], prompt
 
     def _admit_waiting(self) -> None:
-        free = self.slots - len(self.slot_key)
-        while self.waiting and free > 0:
-            got = self._take(free)
+        while self.waiting and len(self.slot_key) < self.slots:
+            got = self._take(self.slots - len(self.slot_key))
             if got is None:
                 break
             keys, ids, bert, prompt = got
             if not self.started:
                 r = self.eng.infer(ids, bert, prompt, max_new_steps=0, reserve_slots=self.slots, reserve_positions=self.positions,
-                                   **self.kw, **self.hooks)
+                                   utt_ids=keys, **self.kw, **self.hooks)
                 self.first_logits = r.logits
                 self.started = True
+                slots = list(range(len(keys)))
             else:
-                self.eng.admit(ids, bert, prompt)
-            self.slot_key += keys
-            self.reported += [False] * len(keys)
-            free -= len(keys)
+                slots = self.eng.admit(ids, bert, prompt, utt_ids=keys)
+            for sl, k in zip(slots, keys):
+                self.slot_key[sl] = k
 
     def __iter__(self) -> Iterator[Tuple[int, torch.Tensor, int]]:
         while True:
             self._admit_waiting()
-            if not self.started:
+            if not self.slot_key:
                 return
             res = self.eng.session_result()
-            pending = False
             seqs = res.sequences()
-            for slot, i in enumerate(res.idx):
-                if i >= 0 and not self.reported[slot]:
-                    self.reported[slot] = True
-                    yield self.slot_key[slot], seqs[slot].clone(), i
-                elif i < 0:
-                    pending = True
-            if not pending:
-                if self.waiting and len(self.slot_key) >= self.slots:
-                    # every slot has been used and all of them have finished: a fresh session takes the rest
-                    self.started = False
-                    self.slot_key, self.reported = [], []
-                    continue
-                if not self.waiting:
-                    return
-                continue
+            finished = [sl for sl in self.slot_key if res.idx[sl] >= 0]
+            for sl in finished:
+                yield self.slot_key.pop(sl), seqs[sl].clone(), res.idx[sl]
+            if finished:
+                self.eng.release(finished)
+                continue  # admit into the freed slots before the next slice
             self.eng.decode_more(self.slice_steps)

@@ -126,6 +126,7 @@ struct Ctx {
   // per-slot session state (continuous batching: t2s_admit adds utterances to a resident session at a later global step)
   int* slot_step0;                      // global step at which the slot's step 0 was sampled (0 for the first request)
   int* slot_P;                          // prompt length of the slot's request
+  int* slot_uid;                        // utterance id keying the slot's Philox stream (default: slot + slot_base)
   const long long* const* slot_prompt;  // the slot's prompt row (caller-owned, alive for the session)
   int* gen;      // [B0][max_steps]
   int* sampled;  // [B0][max_steps]

@@ -92,7 +92,10 @@ struct t2s_engine {
   int cap = 0, maxP = 0, sess_max_pages = 0;           // session geometry: slot capacity, longest prompt, K/V pages per slot
   int session_slots = 0, session_positions = 0;        // options: slots / positions per slot to reserve at t2s_prefill
   size_t next_page = 0;
-  std::vector<int> h_page_table;
+  std::vector<int> h_page_table, h_slot_text_len, h_slot_local, slot_pages;  // host mirrors per slot (pages handed to the slot so far)
+  std::vector<char> slot_free;     // released by t2s_release_slots: t2s_admit reuses them (their K/V pages too) before fresh ones
+  std::vector<int> pending_uids;   // t2s_set_utterance_ids: Philox ids of the next request's utterances
+  DevBuf slot_aux;                 // device: [text length by slot | request-local index by slot]
   DevBuf page_tab, drows, slot_prompt;                 // session-persistent: page table, decode row descriptors, per-slot prompt pointers
   std::vector<int> h_text_len, h_s0;
   int n_qtiles = 0;
@@ -240,7 +243,7 @@ extern "C" void t2s_destroy(t2s_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->wmat, &e->wvec, &e->whead, &e->wbert, &e->bbert, &e->emb_audio, &e->emb_text, &e->pe, &e->wrow,
-                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->wwide, &e->llbuf, &e->page_tab, &e->drows, &e->slot_prompt, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
+                    &e->wrow_g, &e->wrow_head, &e->wrow_head_g, &e->head_c, &e->wstream, &e->hstream, &e->wwide, &e->llbuf, &e->page_tab, &e->drows, &e->slot_prompt, &e->slot_aux, &e->x0b_rows, &e->x0b_slots, &e->yb1, &e->yb2, &e->sp1, &e->sp2,
                     &e->kpool, &e->vpool, &e->ints, &e->ints2, &e->kvoff, &e->attn_desc, &e->x0_rows, &e->x0_slots, &e->q, &e->attn, &e->y1, &e->h,
                     &e->y2, &e->stat2, &e->logits, &e->part, &e->seg_cnt, &e->gen, &e->sampled, &e->seen, &e->misc,
                     &e->bert_rows, &e->xf, &e->xb, &e->in_ids, &e->in_prompt, &e->in_bert, &e->in_bert_ptrs, &e->out_tokens, &e->out_idx, &e->latent_flag};
@@ -519,8 +522,11 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
         early_stop != d.early_stop || rq->eos_suppress_steps != d.eos_window || rq->max_steps != d.max_steps)
       return fail("t2s_admit: sampling parameters / stop rules are per session and must equal those of t2s_prefill");
     slot0 = e->B;
-    if (slot0 + B > e->cap) return fail("t2s_admit: %d more utterances do not fit the session's %d slots (%d in use; reserve them with "
-                                        "T2S_OPT_SESSION_SLOTS before t2s_prefill)", B, e->cap, slot0);
+    int n_free = 0;
+    for (int i = 0; i < e->B; ++i) n_free += e->slot_free[i] ? 1 : 0;
+    if (B > n_free + (e->cap - e->B))
+      return fail("t2s_admit: %d more utterances do not fit the session's %d slots (%d in use, %d of them released; reserve slots with "
+                  "T2S_OPT_SESSION_SLOTS before t2s_prefill, free finished ones with t2s_release_slots)", B, e->cap, e->B, n_free);
     int n_active = 0, aborted = 0;
     if (read_state(e, s, &n_active, &step0, &aborted)) return 1;
     if (aborted) return fail("t2s_admit: the session is in an error state");
@@ -552,11 +558,31 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     return fail("t2s_admit: an utterance needs %d K/V pages, the session was opened with %d per slot (T2S_OPT_SESSION_POSITIONS)", need_pages, e->sess_max_pages);
   }
   const int max_pages = e->sess_max_pages, cap = e->cap;
+  if (!admit) {
+    e->h_slot_text_len.assign(cap, 0); e->h_slot_local.assign(cap, 0); e->slot_pages.assign(cap, 0); e->slot_free.assign(cap, 0);
+  }
+  // the request's utterances -> session slots: a fresh session takes 0..B-1, an admission released slots first (lowest first)
+  std::vector<int> new_slots(B);
+  {
+    int nb = 0;
+    if (admit)
+      for (int i = 0; i < e->B && nb < B; ++i)
+        if (e->slot_free[i]) { new_slots[nb++] = i; e->slot_free[i] = 0; }
+    for (int i = admit ? e->B : 0; nb < B; ++i) new_slots[nb++] = i;
+  }
+  std::vector<int> uids(B);
+  if (!e->pending_uids.empty() && (int)e->pending_uids.size() != B)
+    return fail("%s: t2s_set_utterance_ids gave %zu ids for a batch of %d", who, e->pending_uids.size(), B);
+  for (int b = 0; b < B; ++b) uids[b] = e->pending_uids.empty() ? new_slots[b] + e->slot_base : e->pending_uids[b];
+  e->pending_uids.clear();
   // ---- KV pool + page table (pages handed out contiguously per slot).  A fresh session sizes the pool for its CAPACITY when slots
   //      were reserved (the pool cannot grow under a resident session: its contents are the session), else for what it uses.
   for (int b = 0; b < B; ++b) {
-    const int np = (s0[b] + steps_cap + PAGE - 1) / PAGE;
-    for (int i = 0; i < np; ++i) e->h_page_table[(size_t)(slot0 + b) * max_pages + i] = (int)e->next_page++;
+    const int np = (s0[b] + steps_cap + PAGE - 1) / PAGE, slot = new_slots[b];
+    for (int i = e->slot_pages[slot]; i < np; ++i) e->h_page_table[(size_t)slot * max_pages + i] = (int)e->next_page++;  // a reused slot keeps its pages
+    e->slot_pages[slot] = std::max(e->slot_pages[slot], np);
+    e->h_slot_text_len[slot] = text_len[b];
+    e->h_slot_local[slot] = b;
   }
   {
     const size_t pages = admit ? e->next_page : std::max(e->next_page, (size_t)(cap > B ? (size_t)cap * max_pages : 0));
@@ -574,14 +600,14 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   std::vector<QTile> qtiles;
   for (int b = 0, r = 0, tr = 0; b < B; ++b) {
     for (int j = 0; j < s0[b]; ++j, ++r) {
-      row_slot[r] = slot0 + b; row_pos[r] = j;
+      row_slot[r] = new_slots[b]; row_pos[r] = j;
       if (j < text_len[b]) { trow_slot[tr] = b; trow_j[tr] = j; trow_row[tr] = r; ++tr; }
     }
     head_rows[b] = r - 1;
-    for (int q0 = 0; q0 < s0[b]; q0 += 64) qtiles.push_back(QTile{slot0 + b, q0, row0[b] + q0, std::min(64, s0[b] - q0)});
+    for (int q0 = 0; q0 < s0[b]; q0 += 64) qtiles.push_back(QTile{new_slots[b], q0, row0[b] + q0, std::min(64, s0[b] - q0)});
   }
   const size_t R = (size_t)std::max(T, MAX_B);
-  const size_t n_ints = (size_t)2 * R + B * 5 + (size_t)3 * n_text + qtiles.size() * 4 + 64;
+  const size_t n_ints = (size_t)2 * R + B * 6 + (size_t)3 * n_text + qtiles.size() * 4 + 64;
   int rc = 0;
   rc |= e->ints.ensure(n_ints * 4);
   rc |= e->kvoff.ensure(R * 8);
@@ -600,12 +626,13 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   rc |= e->bert_rows.ensure((size_t)n_text * BERT * 2);
   if (e->prefill_gemm) { rc |= e->xf.ensure((size_t)T * D * 4); rc |= e->xb.ensure((size_t)T * D * 2); }
   if (!admit) {  // session buffers (a resident session's must not move)
-    rc |= e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4);
+    rc |= e->ints2.ensure((size_t)(MAX_B * 7 + 16) * 4);
     rc |= e->gen.ensure((size_t)cap * rq->max_steps * 4);
     rc |= e->sampled.ensure((size_t)cap * rq->max_steps * 4);
     rc |= e->page_tab.ensure((size_t)cap * max_pages * 4);
     rc |= e->drows.ensure((size_t)MAX_B * 16);
     rc |= e->slot_prompt.ensure((size_t)MAX_B * 8);
+    rc |= e->slot_aux.ensure((size_t)MAX_B * 8);
   }
   if (rc) return 1;
   // pack the int arrays into one upload
@@ -618,17 +645,17 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   const size_t o_toff = put(text_off.data(), B);
   const size_t o_tlen = put(text_len.data(), B);
   const size_t o_s0 = put(s0.data(), B);
-  std::vector<int> new_slots(B);
-  for (int b = 0; b < B; ++b) new_slots[b] = slot0 + b;
   const size_t o_new = put(new_slots.data(), B);
+  const size_t o_uid = put(uids.data(), B);
   const size_t o_ts = put(trow_slot.data(), n_text);
   const size_t o_tj = put(trow_j.data(), n_text);
   const size_t o_tr = put(trow_row.data(), n_text);
   o = (o + 3) & ~(size_t)3;
   const size_t o_qt = put(reinterpret_cast<const int*>(qtiles.data()), qtiles.size() * 4);
   CK(cudaMemcpyAsync(e->ints.p, hi.data(), o * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(e->page_tab.as<int>() + (size_t)slot0 * max_pages, page_table.data() + (size_t)slot0 * max_pages,
-                     (size_t)B * max_pages * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->page_tab.p, page_table.data(), (size_t)cap * max_pages * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->slot_aux.p, e->h_slot_text_len.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->slot_aux.as<int>() + MAX_B, e->h_slot_local.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, s));
   std::vector<long long> kvoff(T);
   for (int r = 0; r < T; ++r)
     kvoff[r] = kv_row_off(page_table[(size_t)row_slot[r] * max_pages + (row_pos[r] >> PAGE_SHIFT)], row_pos[r] & (PAGE - 1));
@@ -701,7 +728,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     c.bar = reinterpret_cast<unsigned*>(i2 + 4);
     c.stats = reinterpret_cast<unsigned long long*>(i2 + 8);  // 3 x u64, 8-byte aligned
     c.seq_len = i2 + 16; c.active = i2 + 16 + MAX_B; c.done = i2 + 16 + 2 * MAX_B; c.out_idx = i2 + 16 + 3 * MAX_B;
-    c.slot_step0 = i2 + 16 + 4 * MAX_B; c.slot_P = i2 + 16 + 5 * MAX_B;
+    c.slot_step0 = i2 + 16 + 4 * MAX_B; c.slot_P = i2 + 16 + 5 * MAX_B; c.slot_uid = i2 + 16 + 6 * MAX_B;
     c.slot_prompt = e->slot_prompt.as<const long long*>();
     c.logits = e->logits.as<float>();
     c.part = e->part.as<float>(); c.seg_cnt = e->seg_cnt.as<int>();
@@ -730,7 +757,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   Ctx cpx = c;
   cpx.row_slot = e->d_row_slot; cpx.row_pos = e->d_row_pos; cpx.row_kvoff = e->kvoff.as<long long>();
   cpx.x0 = e->x0_rows.as<float>(); cpx.x0b = e->x0b_rows.as<bf16>(); cpx.x0_by_slot = 0; cpx.head_rows = e->d_head_rows;
-  Ctx cs0 = cd;  // step-0 sampler of the new utterances: logits row b <-> slot slot0 + b
+  Ctx cs0 = cd;  // step-0 sampler of the new utterances: logits row b <-> slot new_slots[b]
   if (admit) {
     int* scratch = reinterpret_cast<int*>(e->misc.as<char>() + 192);  // [n_rows, n_active] of the admitted request
     cpx.n_rows = scratch; cpx.n_active = scratch + 1;
@@ -745,12 +772,12 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   const int g = e->num_sms;
   if (!admit) CK(cudaMemsetAsync(cd.abort_flag, 0, 4, s));
   Ctx ci = cd; ci.P = P;
-  k_init_session<<<B, 128, 0, s>>>(ci, d_prompt, prompt_stride, e->d_s0, slot0, step0, admit ? 0 : 1);
+  k_init_session<<<B, 128, 0, s>>>(ci, d_prompt, prompt_stride, e->d_s0, di + o_new, di + o_uid, step0, admit ? 0 : 1);
   if (!admit) {
     CK(cudaMemcpyAsync(cp.n_rows, &e->T, 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(e->llbuf.p, 0, 64, s));  // wide decode: the tag sequence of the hand-off cells restarts (cells are compared for equality)
   }
-  k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride, slot0);
+  k_embed_rows<<<T, 128, 0, s>>>(cp, T, d_ids, e->d_text_off, e->d_text_len, d_prompt, prompt_stride, e->slot_aux.as<int>() + MAX_B);
   const void* const* dptr = reinterpret_cast<const void* const*>(e->in_bert_ptrs.p);
   const long long* dsc = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 8);
   const long long* dst_ = reinterpret_cast<const long long*>(e->in_bert_ptrs.as<char>() + (size_t)B * 16);
@@ -762,7 +789,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     k_bert_rows<bf16><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
   k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
   e->launches += 4;
-  const int* d_text_len_by_slot = e->d_text_len - slot0;  // the attention kernels index text_len by session slot
+  const int* d_text_len_by_slot = e->slot_aux.as<int>();  // the attention kernels index text_len by session slot
   if (e->prefill_gemm) {
     // tcgen05/TMEM + TMA GEMMs (gemm_tc.cuh); LayerNorm rows are materialised once per sub-layer
     float* xf = e->xf.as<float>();
@@ -814,7 +841,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   launch_phase<PH_HEAD>(e, cp, 0, g, s);            // rows = the request's B utterances, gathered through head_rows
   launch_phase<PH_SAMPLE>(e, cs0, 0, std::min(B, g), s);  // step 0 sample of the new utterances; writes the decode-side x0
   if (admit) {
-    k_admit<<<1, 256, 0, s>>>(e->cd, slot0, B);
+    k_admit<<<1, 256, 0, s>>>(e->cd, di + o_new, B);
     e->launches++;
   } else {
     launch_phase<PH_PLAN>(e, e->cd, 0, 1, s);
@@ -831,7 +858,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   if (admit) {
     e->st.prefill_ms += ms;
     e->st.prefill_rows += T;
-    e->B = slot0 + B;
+    for (int b = 0; b < B; ++b) e->B = std::max(e->B, new_slots[b] + 1);
   } else {
     e->st.prefill_ms = ms;
     e->st.decode_ms = 0.0;
@@ -854,6 +881,29 @@ extern "C" int t2s_prefill(t2s_engine* e, const t2s_request* rq, void* stream_) 
 extern "C" int t2s_admit(t2s_engine* e, const t2s_request* rq, void* stream_) {
   if (!e || !rq) return fail("t2s_admit: null argument");
   return prefill_impl(e, rq, (cudaStream_t)stream_, true);
+}
+
+extern "C" int t2s_release_slots(t2s_engine* e, const int32_t* slots, int32_t n, void* stream_) {
+  if (!e || (n > 0 && !slots)) return fail("t2s_release_slots: null argument");
+  if (!e->session) return fail("t2s_release_slots: no resident session");
+  cudaStream_t s = (cudaStream_t)stream_;
+  std::vector<int> done(e->B);
+  CK(cudaMemcpyAsync(done.data(), e->cd.done, (size_t)e->B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    const int sl = slots[i];
+    if (sl < 0 || sl >= e->B) return fail("t2s_release_slots: slot %d is not in use (0..%d)", sl, e->B - 1);
+    if (!done[sl]) return fail("t2s_release_slots: slot %d is still decoding", sl);
+    if (e->slot_free[sl]) return fail("t2s_release_slots: slot %d was already released", sl);
+  }
+  for (int i = 0; i < n; ++i) e->slot_free[slots[i]] = 1;
+  return 0;
+}
+
+extern "C" int t2s_set_utterance_ids(t2s_engine* e, const int32_t* ids, int32_t n) {
+  if (!e || (n > 0 && !ids)) return fail("t2s_set_utterance_ids: null argument");
+  e->pending_uids.assign(ids, ids + std::max(n, 0));
+  return 0;
 }
 
 // ---- decode ----------------------------------------------------------------------------------------------
@@ -1104,7 +1154,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   cudaStream_t s = (cudaStream_t)stream_;
   e->session = false;  // clobbers the session state
   const int ms = step + 2;
-  if (e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4) || e->gen.ensure((size_t)n * ms * 4 * 3)) return 1;
+  if (e->ints2.ensure((size_t)(MAX_B * 7 + 16) * 4) || e->gen.ensure((size_t)n * ms * 4 * 3)) return 1;
   std::vector<float> lg((size_t)n * VPAD, 0.f);
   for (int r = 0; r < n; ++r) memcpy(&lg[(size_t)r * VPAD], logits + (size_t)r * V, V * 4);
   std::vector<uint32_t> seen((size_t)n * SEEN_WORDS, 0u);
@@ -1113,7 +1163,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
       const int t = prev ? prev[(size_t)r * m + j] : -1;
       if (t >= 0 && t < V) seen[(size_t)r * SEEN_WORDS + (t >> 5)] |= 1u << (t & 31);
     }
-  std::vector<int> i2(16 + 6 * MAX_B, 0);  // ... + slot_step0 (0) + slot_P (0)
+  std::vector<int> i2(16 + 7 * MAX_B, 0);  // ... + slot_step0 (0) + slot_P (0) + slot_uid (0: the test's Philox stream is utterance 0)
   i2[0] = n; i2[1] = n; i2[2] = step;
   for (int r = 0; r < n; ++r) i2[16 + MAX_B + r] = r;  // active = identity
   CK(cudaMemcpyAsync(e->logits.p, lg.data(), lg.size() * 4, cudaMemcpyHostToDevice, s));
@@ -1123,7 +1173,7 @@ extern "C" int t2s_sampler_test(t2s_engine* e, const float* logits, int32_t n, i
   int* d2 = e->ints2.as<int>();
   c.n_rows = d2; c.n_active = d2 + 1; c.step = d2 + 2; c.abort_flag = d2 + 3;
   c.seq_len = d2 + 16; c.active = d2 + 16 + MAX_B; c.done = d2 + 16 + 2 * MAX_B; c.out_idx = d2 + 16 + 3 * MAX_B;
-  c.slot_step0 = d2 + 16 + 4 * MAX_B; c.slot_P = d2 + 16 + 5 * MAX_B;
+  c.slot_step0 = d2 + 16 + 4 * MAX_B; c.slot_P = d2 + 16 + 5 * MAX_B; c.slot_uid = d2 + 16 + 6 * MAX_B;
   c.logits = e->logits.as<float>(); c.seen = e->seen.as<uint32_t>();
   c.gen = e->gen.as<int>(); c.sampled = c.gen + (size_t)n * ms; c.greedy_rec = c.gen + (size_t)2 * n * ms;
   c.B0 = n; c.P = 0; c.max_steps = ms; c.eos_window = (width == V) ? 0 : step + 1; c.early_stop = -1; c.top_k = top_k;
@@ -1148,7 +1198,7 @@ extern "C" int t2s_set_timeline(t2s_engine* e, long long* buf, int32_t step, int
 extern "C" int t2s_bench_barrier(t2s_engine* e, int32_t n_barriers, int32_t n_ctas, float* ms_out, void* stream_) {
   if (!e || !ms_out || n_barriers < 1) return fail("t2s_bench_barrier: bad argument");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (e->ints2.ensure((size_t)(MAX_B * 6 + 16) * 4)) return 1;
+  if (e->ints2.ensure((size_t)(MAX_B * 7 + 16) * 4)) return 1;
   int* i2 = e->ints2.as<int>();
   CK(cudaMemsetAsync(i2, 0, 64, s));
   unsigned* bar = reinterpret_cast<unsigned*>(i2 + 4);

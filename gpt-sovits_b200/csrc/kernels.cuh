@@ -93,13 +93,14 @@ __global__ void __launch_bounds__(NT, 1) k_barrier_bench(unsigned* counter, int*
 }
 
 // ---- session initialisation ----------------------------------------------------------------------------
-// One CTA per utterance of the request: local index b = blockIdx.x, session slot = slot0 + b.  seen-bitmap from the prompt
+// One CTA per utterance of the request: local index b = blockIdx.x, session slot = slots[b] (fresh session: b; t2s_admit: free
+// slots, released ones first).  seen-bitmap from the prompt
 // (previous_tokens = y includes the prompt, t2s_model.py:714), per-slot counters.  fresh = 1: a new session (global counters
 // reset, identity active list); fresh = 0: t2s_admit adds the utterances to the resident session at global step `step0`
 // (k_admit appends them to the active list after their prefill).
-__global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_row_stride, const int* s0, int slot0, int step0,
-                               int fresh) {
-  const int b = blockIdx.x, tid = threadIdx.x, slot = slot0 + b;
+__global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_row_stride, const int* s0, const int* slots,
+                               const int* uids, int step0, int fresh) {
+  const int b = blockIdx.x, tid = threadIdx.x, slot = slots[b];
   __shared__ unsigned bits[SEEN_WORDS];
   if (tid < SEEN_WORDS) bits[tid] = 0u;
   __syncthreads();
@@ -116,6 +117,7 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
     c.seq_len[slot] = s0[b];
     c.slot_step0[slot] = step0;
     c.slot_P[slot] = c.P;
+    c.slot_uid[slot] = uids[b];
     const_cast<const long long**>(c.slot_prompt)[slot] = prompt + (long long)b * prompt_row_stride;
     c.seg_cnt[slot] = 0;
     if (fresh) {
@@ -132,11 +134,11 @@ __global__ void k_init_session(Ctx c, const long long* prompt, long long prompt_
 // t2s_admit, after the new utterances' prefill and step-0 sample: append those that did not stop at once to the active list
 // and give them the row descriptors phase_plan would have produced (their first decode step is the session's next step).
 // One CTA; n_new <= MAX_B.
-__global__ void k_admit(Ctx c, int slot0, int n_new) {
+__global__ void k_admit(Ctx c, const int* slots, int n_new) {
   __shared__ int keep_s[MAX_B];
   __shared__ int base_s;
   const int tid = threadIdx.x;
-  for (int i = tid; i < n_new; i += blockDim.x) keep_s[i] = ld_cg_i(c.done + slot0 + i) ? 0 : 1;
+  for (int i = tid; i < n_new; i += blockDim.x) keep_s[i] = ld_cg_i(c.done + slots[i]) ? 0 : 1;
   __syncthreads();
   if (tid == 0) {
     const int n_old = ld_cg_i(c.n_active);
@@ -159,7 +161,7 @@ __global__ void k_admit(Ctx c, int slot0, int n_new) {
   for (int i = tid; i < n_new; i += blockDim.x) {
     const int p = keep_s[i];
     if (p < 0) continue;
-    const int slot = slot0 + i, pos = ld_cg_i(c.seq_len + slot);
+    const int slot = slots[i], pos = ld_cg_i(c.seq_len + slot);
     c.active[p] = slot;
     c.row_slot[p] = slot;
     c.row_pos[p] = pos;
@@ -173,10 +175,10 @@ __global__ void k_admit(Ctx c, int slot0, int n_new) {
 // Row r = (slot, j).  Text rows:  emb_text[ph] + bert_proj.bias + alpha_t*pe[j]   (+ bert_proj GEMM, added
 // afterwards by the OUT_BERT projection phase);  audio rows: emb_audio[tok] + alpha_a*pe[j - L].
 __global__ void k_embed_rows(Ctx c, int n_rows, const long long* phoneme_ids, const int* text_off,
-                             const int* text_len, const long long* prompt, long long prompt_row_stride, int slot0) {
+                             const int* text_len, const long long* prompt, long long prompt_row_stride, const int* slot_local) {
   const int r = blockIdx.x;
   if (r >= n_rows) return;
-  const int slot = c.row_slot[r] - slot0, j = c.row_pos[r], L = text_len[slot];  // request-local utterance index
+  const int slot = slot_local[c.row_slot[r]], j = c.row_pos[r], L = text_len[slot];  // request-local utterance index
   float* out = c.x0 + (size_t)r * D;
   if (j < L) {
     long long ph = phoneme_ids[text_off[slot] + j];

@@ -810,7 +810,7 @@ __device__ bool sample_row(const Ctx& c, int r, int gstep, SampSmem& sm, int slo
     bool valid[SV];
     uint32_t sw[SV];  // the "seen" words of the repetition penalty: requested together with the logits (one L2 round trip)
     const uint32_t* seen = c.seen + (size_t)slot * SEEN_WORDS;
-    const int step0 = ld_cg_i(c.slot_step0 + slot), P = ld_cg_i(c.slot_P + slot);  // in flight with the logits
+    const int step0 = ld_cg_i(c.slot_step0 + slot), P = ld_cg_i(c.slot_P + slot), uid = ld_cg_i(c.slot_uid + slot);  // in flight with the logits
 #pragma unroll
     for (int j = 0; j < SV; ++j) {
       const int i = tid + NT * j;
@@ -876,7 +876,7 @@ __device__ bool sample_row(const Ctx& c, int r, int gstep, SampSmem& sm, int slo
         // (the winner is the same as if every element had drawn one)
         if (!valid[j] || e[j] == 0.f) continue;
         uint32_t w[4];
-        philox4x32_10((uint32_t)(i >> 2), (uint32_t)step, (uint32_t)(slot + c.slot_base), 0u, c.seed_lo, c.seed_hi, w);
+        philox4x32_10((uint32_t)(i >> 2), (uint32_t)step, (uint32_t)uid, 0u, c.seed_lo, c.seed_hi, w);
         const uint32_t word = w[i & 3];
         const float u = ((float)(word >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
         const float q = -logf(u);

@@ -214,11 +214,14 @@ class T2SEngine:
         host_io: bool = False,
         reserve_slots: int = 0,
         reserve_positions: int = 0,
+        utt_ids: Optional[Sequence[int]] = None,
     ) -> InferResult:
         """phoneme_ids: B tensors [L_i] int64; bert: B tensors [1024, L_i]; prompt: [B, P] int64 or None.
         host_io=True takes CPU tensors and returns CPU tokens: the H2D / D2H copies happen inside the
         C-ABI call (bench.py's end-to-end leg).  reserve_slots / reserve_positions > 0 open the session with room for
-        later ``admit()`` calls (continuous batching): that many slots in total, that many K/V positions per slot."""
+        later ``admit()`` calls (continuous batching): that many slots in total, that many K/V positions per slot.
+        utt_ids: one integer per utterance keying its Philox stream (default: its index in this call), so that sampling does not
+        depend on how a caller shards or batches the utterances."""
         rq, keep, B, P = self._request(phoneme_ids, bert, prompt, top_k, top_p, temperature, repetition_penalty, early_stop_num,
                                        eos_suppress_steps, max_steps, seed, host_io)
         ids, bert, prompt = keep
@@ -227,6 +230,8 @@ class T2SEngine:
         self.set_option(_lib.OPT_SESSION_SLOTS, int(reserve_slots))
         self.set_option(_lib.OPT_SESSION_POSITIONS, int(reserve_positions))
         self._slot_P = [P] * B
+        self._free: List[int] = []
+        self._set_utt_ids(utt_ids, B)
         self._session_kw = dict(top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
                                 early_stop_num=early_stop_num, eos_suppress_steps=eos_suppress_steps, max_steps=max_steps, seed=seed)
         self._max_steps = int(max_steps)
@@ -268,20 +273,47 @@ class T2SEngine:
                 res.sampled = samp
         return res
 
-    def admit(self, phoneme_ids: Sequence[torch.Tensor], bert: Sequence[torch.Tensor], prompt: Optional[torch.Tensor]) -> List[int]:
+    def _set_utt_ids(self, utt_ids, B: int) -> None:
+        if utt_ids is None:
+            _lib.check(self.lib.t2s_set_utterance_ids(self._h, None, 0))
+            return
+        if len(utt_ids) != B:
+            raise ValueError("utt_ids must have one entry per utterance")
+        arr = (C.c_int32 * B)(*[int(v) & 0x7FFFFFFF for v in utt_ids])
+        _lib.check(self.lib.t2s_set_utterance_ids(self._h, arr, B))
+
+    def release(self, slots: Sequence[int]) -> None:
+        """Hands the slots of FINISHED utterances back to the resident session (after their tokens were fetched): the next
+        ``admit()`` reuses them and their K/V pages (C ABI: t2s_release_slots)."""
+        arr = (C.c_int32 * len(slots))(*[int(v) for v in slots])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.t2s_release_slots(self._h, arr, len(slots), self._stream()))
+        self._free = sorted(set(self._free) | set(int(v) for v in slots))
+
+    def admit(self, phoneme_ids: Sequence[torch.Tensor], bert: Sequence[torch.Tensor], prompt: Optional[torch.Tensor],
+              utt_ids: Optional[Sequence[int]] = None) -> List[int]:
         """Continuous batching: adds utterances to the resident session (opened by ``infer(..., max_new_steps=k,
-        reserve_slots=n)``) at its current step; returns their slot indices (= their rows in ``result()``).  Sampling parameters
-        and stop rules are the session's; the prompt may differ from the first request's (C ABI: t2s_admit)."""
+        reserve_slots=n)``) at its current step; returns their slot indices (= their rows in ``result()``): released slots
+        first, lowest first, then fresh ones.  Sampling parameters and stop rules are the session's; the prompt may differ from
+        the first request's (C ABI: t2s_admit)."""
         kw = self._session_kw
         rq, keep, B, P = self._request(phoneme_ids, bert, prompt, kw["top_k"], kw["top_p"], kw["temperature"],
                                        kw["repetition_penalty"], kw["early_stop_num"], kw["eos_suppress_steps"], kw["max_steps"],
                                        kw["seed"] if kw["seed"] is not None else 0, False)
+        self._set_utt_ids(utt_ids, B)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.t2s_admit(self._h, C.byref(rq), self._stream()))
         self._keep.append(keep)
-        first = len(self._slot_P)
-        self._slot_P += [P] * B
-        return list(range(first, first + B))
+        slots = []
+        for _ in range(B):  # the C side's order: released slots first (ascending), then fresh ones
+            if self._free:
+                sl = self._free.pop(0)
+                self._slot_P[sl] = P
+            else:
+                sl = len(self._slot_P)
+                self._slot_P.append(P)
+            slots.append(sl)
+        return slots
 
     def session_result(self) -> InferResult:
         """``result()`` for every slot of the resident session, admitted ones included."""

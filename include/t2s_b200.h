@@ -114,6 +114,14 @@ int t2s_prefill(t2s_engine* e, const t2s_request* req, void* stream);
  * the prompt length may differ.  Device inputs only; the prompt rows must stay valid for the session.  New slots follow the
  * existing ones in t2s_result's order. */
 int t2s_admit(t2s_engine* e, const t2s_request* req, void* stream);
+/* Returns the slots of FINISHED utterances (idx >= 0 in t2s_result; fetch their tokens first) to the session: the next
+ * t2s_admit reuses them - and their K/V pages - before it takes fresh slots, so a resident session serves an unbounded
+ * stream of utterances with a fixed number of slots.  A slot that is still decoding is an error. */
+int t2s_release_slots(t2s_engine* e, const int32_t* slots, int32_t n, void* stream);
+/* The utterances of the NEXT t2s_prefill / t2s_admit get these ids (host array, one per utterance) as the key of their Philox
+ * streams instead of their slot index: sampling then does not depend on which slot, chunk, session or GPU an utterance lands in
+ * (gpt-sovits_b200/shard.py passes the position in the caller's batch, StreamingSession the submission order). */
+int t2s_set_utterance_ids(t2s_engine* e, const int32_t* ids, int32_t n);
 
 /* The decode loop (t2s_model.py:701-769 / :878-914) for at most max_new_steps further steps
  * (-1: until every sequence has stopped).  Synchronises `stream`.  steps_run = steps executed. */
