@@ -395,8 +395,8 @@ extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
   switch (opt) {
     case T2S_OPT_DECODE_MODE: if (v < 0 || v > 6) return fail("decode mode must be 0 .. 6"); e->decode_mode = (int)v; break;
     case T2S_OPT_PREFILL_GEMM:
-      if (v != 0 && v != 1) return fail("prefill gemm must be 0 or 1");
-      if (v == 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
+      if (v < 0 || v > 2) return fail("prefill gemm must be 0, 1 or 2");
+      if (v >= 1 && !e->tc_ok) return fail("tcgen05 GEMM unavailable: cuTensorMapEncodeTiled entry point not found");
       e->prefill_gemm = (int)v; break;
     case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
     case T2S_OPT_TC_DECODE_MIN_BATCH: if (v < 0 || v > 100000) return fail("tc_decode_min_batch out of range"); e->tc_decode_min_batch = (int)v; break;
@@ -796,6 +796,12 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     bf16* xb = e->xb.as<bf16>();
     const int ln_blocks = (T + 7) / 8;
     bool ok = true;
+    // 1: persistent kernel (128 x 256 tiles, operand ring across tiles, two TMEM accumulators); 2: one 128 x 128 tile per CTA (round 1)
+    const bool persistent = e->prefill_gemm == 1;
+    const int T_ = T, nsm = e->num_sms;
+    auto gemm = [&](const bf16* A, const bf16* W, int N, int K, const TcEpilogue& ep) {
+      return persistent ? launch_gemm_tcp<256>(A, W, T_, N, K, ep, nsm, s) : launch_gemm_tc<128>(A, W, T_, N, K, ep, s);
+    };
     for (int l = 0; l < cp.n_layer && ok; ++l) {
       const float* vl = cp.wvec + (size_t)l * LV;
       const bf16* wr = e->wrow.as<bf16>() + (size_t)l * LW;
@@ -812,17 +818,17 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
       ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
-      ok = ok && launch_gemm_tc<128>(xb, wr + OFF_WQKV, T, 3 * D, D, ep, s);
+      ok = ok && gemm(xb, wr + OFF_WQKV, 3 * D, D, ep);
       k_prefill_attn_tc<<<dim3(e->n_qtiles, NH), 128, 0, s>>>(cp, l, e->d_qtiles, d_text_len_by_slot);
       ep = TcEpilogue{};
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;
-      ok = ok && launch_gemm_tc<128>(cp.attn, wr + OFF_WO, T, D, D, ep, s);
+      ok = ok && gemm(cp.attn, wr + OFF_WO, D, D, ep);
       k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.y1, vl + VO_G1, vl + VO_BE1, xf, xb, T, 1);
       ep.mode = EPI_RELU; ep.bias = vl + VO_B1; ep.resid = nullptr; ep.out_f32 = nullptr; ep.out_b16 = cp.h;
-      ok = ok && launch_gemm_tc<128>(xb, wr + OFF_W1, T, FF, D, ep, s);
+      ok = ok && gemm(xb, wr + OFF_W1, FF, D, ep);
       ep.mode = EPI_RESID; ep.bias = vl + VO_B2; ep.resid = xf; ep.out_f32 = cp.y2; ep.out_b16 = nullptr;
-      ok = ok && launch_gemm_tc<128>(cp.h, wr + OFF_W2, T, D, FF, ep, s);
+      ok = ok && gemm(cp.h, wr + OFF_W2, D, FF, ep);
       e->launches += 7;
     }
     if (!ok) return fail("%s: cuTensorMapEncodeTiled failed", who);

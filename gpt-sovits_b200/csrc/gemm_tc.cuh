@@ -63,6 +63,7 @@ struct TcEpilogue {
   const float* g;          // EPI_D_O: previous norm2 gamma/beta; EPI_D_FFN2: this layer's norm1 gamma/beta
   const float* be;
   const float* b2;         // EPI_D_FFN2: linear2.bias
+  int dbg;                 // measurement only (scripts/mb_gemm.cu): 1 = no global stores, 2 = no staging either, 4 = no prefetch loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -277,6 +278,231 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 }
 
+// =====================================================================================================================
+// Persistent variant for the prefill projections (thousands of rows): one CTA per SM walks output tiles of 128 rows x BN
+// columns (BN = 256: 384 operand rows per k-block for 256 columns, and an M = 128, N = 256 tcgen05.mma reads 96 B of operands
+// per clock from shared memory where N = 128 reads 128 B - the full shared-memory bandwidth), with
+//   * a shared-memory operand ring that keeps running ACROSS tiles (the producer is up to STAGES k-blocks ahead, so the
+//     next tile's first operands land while the current tile's last MMAs run),
+//   * TWO accumulators in TMEM (2 x BN of the 512 columns): the MMAs of tile i+1 run while the epilogue drains tile i,
+//   * epilogue warps (TCP_EPI_WARPS / 4 per TMEM lane quarter, an equal share of the columns each) that re-stage every 32 x 32 fp32
+//     block through shared memory so that global reads (residual) and writes are 128-byte row segments instead of one 64-byte piece
+//     per thread and row (the non-persistent kernel's epilogue was LSU-bound: 32 different lines per store instruction); the
+//     loads of a block (bias, residual) are requested one block ahead.
+// Measured (scripts/mb_gemm.cu): the main loop alone runs at 1.25-1.4 PFLOP/s; with the epilogue's stores the
+// projections are bound by the write path (L2 / HBM), not by the tensor pipe or the operand stream.  A weight-stationary
+// variant (a CTA keeps one 128-column block of W in shared memory and streams only A) was built and measured SLOWER (0.81-0.84
+// PFLOP/s main loop: N = 128 MMAs are shared-memory-bandwidth bound) and removed.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2.. epilogue (TMEM lane quarter = warp % 4).
+// Epilogues: EPI_QKV, EPI_RESID, EPI_RELU (the three of T2SBlock.process_prompt, t2s_model.py:135-174).
+constexpr int TCP_EPI_WARPS = 4, TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;  // 8 (two per lane quarter) measured: no faster, and 204 registers spill
+template <int BN> struct TcpCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2, W_BYTES = BN * TC_BK * 2;    // one k-block of A (16 KB) / of W
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;                          // 48 KB (BN = 256) / 32 KB (BN = 128)
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STG_BYTES = TCP_EPI_WARPS * 32 * 128;                     // one swizzled 32 x 32 fp32 block per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  static constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+           TcEpilogue ep) {
+  using CF = TcpCfg<BN>;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int NST = CF::STAGES;
+  unsigned char* stg_all = smem + NST * CF::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + CF::STG_BYTES);
+  // barriers: full[NST] | empty[NST] | acc_full[2] | acc_empty[2]
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NST), accf0 = smem_u32(bars + 2 * NST), acce0 = smem_u32(bars + 2 * NST + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = K / TC_BK;
+  const int n_tiles_n = N / BN, n_tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles_n;
+  // tile t = (row tile t / n_tiles_n, column tile t % n_tiles_n): CTAs that run side by side share the rows of A through L2
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accf0 + 8 * a, 1); mbar_init(acce0 + 8 * a, TCP_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(CF::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: k-block counter `it` runs over all tiles of this CTA =====
+      unsigned it = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x) {
+        const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const unsigned s = it % NST, ph = (it / NST) & 1u;
+          if (!mbar_wait(empty0 + 8 * s, ph ^ 1u, ep.error_flag)) { ok = false; break; }
+          const uint32_t sa = smem_u32(smem + s * CF::STAGE_BYTES);
+          mbar_expect_tx(full0 + 8 * s, CF::STAGE_BYTES);
+          tma_load_2d(sa, &map_a, kb * TC_BK, m0, full0 + 8 * s);
+          tma_load_2d(sa + CF::A_BYTES, &map_w, kb * TC_BK, n0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: accumulator (tile count & 1), columns [acc * BN, acc * BN + BN) =====
+      unsigned it = 0, lt = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++lt) {
+        const unsigned acc = lt & 1u, aph = (lt >> 1) & 1u;
+        if (!mbar_wait(acce0 + 8 * acc, aph ^ 1u, ep.error_flag)) break;  // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const unsigned s = it % NST, ph = (it / NST) & 1u;
+          if (!mbar_wait(full0 + 8 * s, ph, ep.error_flag)) { ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * CF::STAGE_BYTES), sb = sa + CF::A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_ss(tacc, da + 2 * k, db + 2 * k, CF::IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty0 + 8 * s);
+        }
+        if (ok) umma_commit(accf0 + 8 * acc);
+      }
+    }
+  } else {  // ===== epilogue warps: TMEM lane quarter warp % 4, column share (warp - 2) / 4 =====
+    const int wq = warp & 3, ch = (warp - 2) >> 2;
+    constexpr int CW = BN / (TCP_EPI_WARPS / 4);  // columns per warp
+    // staging block: row r = 128 B = eight 16-byte chunks, chunk c stored at position c ^ (r & 7): the row-per-thread writes, the
+    // (row, chunk)-per-lane fp32 reads and the (row, chunk pair)-per-lane bf16 reads are all bank-conflict free
+    unsigned char* stg = stg_all + (warp - 2) * 32 * 128;
+    // fp32 blocks: lane -> (row r4 + 4 i, chunk c4); bf16 blocks: lane -> (row r8 + 8 i, chunks 2 c8, 2 c8 + 1)
+    const int r4 = lane >> 3, c4 = lane & 7, r8 = lane >> 2, c8 = lane & 3;
+    // The global loads of a column block (the lane's bias pieces; the residual pieces of EPI_RESID) are requested ONE BLOCK AHEAD - for
+    // a tile's first block before the wait on its accumulator - so their latency hides behind the previous block's stores.
+    float4 rs[8], bA, bB;  // current block: residual pieces; bias of the lane's columns (fp32 mapping: bA; bf16 mapping: bA, bB)
+    auto prefetch = [&](int t, int c0, float4 (&r)[8], float4& b0, float4& b1) {
+      const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
+      const int f0 = n0 + c0, rbase = m0 + wq * 32;
+      const bool f32map = ep.mode == EPI_RESID || (ep.mode == EPI_QKV && f0 < D);
+      if (f32map) { b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + c4); b1 = b0; }
+      else { b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + 2 * c8); b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + 2 * c8 + 1); }
+      if (ep.mode == EPI_RESID) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rbase + r4 + 4 * i;
+          r[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(ep.resid + (size_t)row * N + f0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, ch * CW, rs, bA, bB);
+    unsigned lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
+      const unsigned acc = lt & 1u, aph = (lt >> 1) & 1u;
+      const int rbase = m0 + wq * 32;            // first row of this warp's 32-row band
+      const int row_t = rbase + lane;            // row held by this thread in the TMEM phase
+      long long kvo = 0;
+      if (ep.mode == EPI_QKV && n0 >= D && row_t < M) kvo = ep.kvoff[row_t];
+      if (!mbar_wait(accf0 + 8 * acc, aph, ep.error_flag)) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = ch * CW; c0 < (ch + 1) * CW; c0 += 32) {
+        const int f0 = n0 + c0;
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const bool last = c0 + 32 >= (ch + 1) * CW;
+        if (last) {  // this warp's part of the accumulator is read: hand it back to the MMA issuer before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(acce0 + 8 * acc);
+        }
+        float4 rn[8], bAn = bA, bBn = bB;  // next block's loads, in flight during this block's staging and stores
+        const bool more = !last || t + (int)gridDim.x < n_tiles;
+        if (more && !(ep.dbg & 4)) prefetch(last ? t + gridDim.x : t, last ? ch * CW : c0 + 32, rn, bAn, bBn);
+        if (ep.dbg & 2) continue;
+        {
+          unsigned char* d = stg + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(d + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+        if (ep.dbg & 1) continue;
+        if (ep.mode == EPI_RESID || (ep.mode == EPI_QKV && f0 < D)) {
+          float* out = ep.out_f32;
+          const int ld = ep.mode == EPI_RESID ? N : D;
+          const float sc = ep.mode == EPI_QKV ? QSCALE : 1.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = r4 + 4 * i, row = rbase + rl;
+            float4 x = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            x.x += bA.x; x.y += bA.y; x.z += bA.z; x.w += bA.w;
+            if (ep.mode == EPI_RESID) { x.x += rs[i].x; x.y += rs[i].y; x.z += rs[i].z; x.w += rs[i].w; }
+            else { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
+            if (row < M) *(reinterpret_cast<float4*>(out + (size_t)row * ld + f0) + c4) = x;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = r8 + 8 * i, row = rbase + rl;
+            float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + (((2 * c8) ^ (rl & 7)) << 4));
+            float4 b = *reinterpret_cast<const float4*>(stg + rl * 128 + (((2 * c8 + 1) ^ (rl & 7)) << 4));
+            a.x += bA.x; a.y += bA.y; a.z += bA.z; a.w += bA.w;
+            b.x += bB.x; b.y += bB.y; b.z += bB.z; b.w += bB.w;
+            if (ep.mode == EPI_RELU) {
+              const uint4 o = make_uint4(pack_bf2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), pack_bf2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)),
+                                         pack_bf2(fmaxf(b.x, 0.f), fmaxf(b.y, 0.f)), pack_bf2(fmaxf(b.z, 0.f), fmaxf(b.w, 0.f)));
+              if (row < M) *(reinterpret_cast<uint4*>(ep.out_b16 + (size_t)row * N + f0) + c8) = o;
+            } else {  // EPI_QKV, k or v: the 32 columns are one head row (64 B) of the K/V page, 16-byte chunks swizzled by position
+              const long long ko = __shfl_sync(0xffffffffu, kvo, rl);
+              const int fk = (f0 < 2 * D ? f0 - D : f0 - 2 * D) + c8 * 8;
+              bf16* base = (f0 < 2 * D ? ep.kpool : ep.vpool) + ep.layer_off + (size_t)ko;
+              const uint4 o = make_uint4(pack_bf2(a.x, a.y), pack_bf2(a.z, a.w), pack_bf2(b.x, b.y), pack_bf2(b.z, b.w));
+              if (row < M) *reinterpret_cast<uint4*>(base + kv_feat(ko, fk)) = o;
+            }
+          }
+        }
+        __syncwarp();  // the staging block is rewritten by the next column block
+        bA = bAn; bB = bBn;
+        if (ep.mode == EPI_RESID) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rs[i] = rn[i];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CF::TMEM_COLS) : "memory");
+  }
+}
+
 // LayerNorm (or plain copy) of fp32 rows -> fp32 + bf16 copies, one warp per row: feeds the GEMM's A operand
 // and its residual (F.layer_norm, t2s_model.py:165-173).
 __global__ void k_ln_rows(const float* __restrict__ in, const float* __restrict__ g, const float* __restrict__ b,
@@ -334,6 +560,8 @@ static inline bool gemm_tc_init() {
   cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tcp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpCfg<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tcp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpCfg<128>::SMEM_BYTES);
   return true;
 }
 
@@ -355,6 +583,16 @@ static inline bool launch_gemm_tc(const bf16* A, const bf16* W, int M, int N, in
   if (!make_tmap_bf16(&ma, A, (uint64_t)M, (uint64_t)K, TC_BM) || !make_tmap_bf16(&mw, W, (uint64_t)N, (uint64_t)K, BN)) return false;
   dim3 grid((M + TC_BM - 1) / TC_BM, N / BN);
   k_gemm_tc<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, s>>>(ma, mw, M, N, K, ep);
+  return true;
+}
+
+// persistent variant (prefill): grid = min(tiles, SMs), tiles of 128 x BN
+template <int BN>
+static inline bool launch_gemm_tcp(const bf16* A, const bf16* W, int M, int N, int K, const TcEpilogue& ep, int num_sms, cudaStream_t s) {
+  CUtensorMap ma, mw;
+  if (!make_tmap_bf16(&ma, A, (uint64_t)M, (uint64_t)K, TC_BM) || !make_tmap_bf16(&mw, W, (uint64_t)N, (uint64_t)K, BN)) return false;
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / BN);
+  k_gemm_tcp<BN><<<tiles < num_sms ? tiles : num_sms, TCP_THREADS, TcpCfg<BN>::SMEM_BYTES, s>>>(ma, mw, M, N, K, ep);
   return true;
 }
 

@@ -189,7 +189,7 @@ enum {
                                 6: "wide" small-batch kernel (<= 8 sequences): every layer spread over 144 SMs, weights
                                    through a TMA shared-memory ring, hand-offs through L2 {value, tag} cells; parity-green
                                    but measured slower than mode 4, so auto never picks it */
-  T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1: tcgen05/TMEM + TMA GEMM */
+  T2S_OPT_PREFILL_GEMM = 1,  /* 0: warp-MMA row-tile projections; 1 (default): persistent tcgen05/TMEM + TMA GEMM; 2: one tile per CTA */
   T2S_OPT_NUM_CTAS = 2,      /* persistent grid size (0 = one CTA per SM) */
   T2S_OPT_CHECK_STEPS = 3,   /* graph mode: host checks the active count every this many steps */
   T2S_OPT_TC_DECODE_MIN_BATCH = 4, /* batch size from which decode projections run on tcgen05 (default 160, the measured crossover; 0: never) */

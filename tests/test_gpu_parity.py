@@ -360,10 +360,12 @@ def test_bitwise_reproducible_and_modes_identical(engine, golden_dir):
     print(f"cluster-stream vs phase kernels (free-running sampled run, first divergence amplifies): max |dlogit| over steps = {d:.4f}")
 
 
+@pytest.mark.parametrize("gemm", [1, 2])
 @pytest.mark.parametrize("case,window", [("naive_b1", 11), ("batch_b4", 1)])
-def test_prefill_tcgen05_gemm(engine, golden_dir, case, window):
-    """Prefill with the tcgen05/TMEM + TMA GEMMs (T2S_OPT_PREFILL_GEMM=1): teacher-forced logits within the
-    tolerance of the reference goldens, and close to the warp-MMA prefill path (different summation order)."""
+def test_prefill_tcgen05_gemm(engine, golden_dir, case, window, gemm):
+    """Prefill with the tcgen05/TMEM + TMA GEMMs (T2S_OPT_PREFILL_GEMM = 1: the persistent 128 x 256-tile kernel, the default;
+    2: round 1's one-tile-per-CTA kernel): teacher-forced logits within the tolerance of the reference goldens, and close to
+    the warp-MMA prefill path (different summation order)."""
     from gpt_sovits_b200 import _lib
     g = _golden(golden_dir, case)
     ids, bert, prompt = _inputs(g)
@@ -371,16 +373,16 @@ def test_prefill_tcgen05_gemm(engine, golden_dir, case, window):
     forced = torch.from_numpy(g["y"][:, P:]).to(torch.int32)
     n = g["logits"].shape[0]
     kw = dict(top_k=1, early_stop_num=int(g["early_stop_num"]), eos_suppress_steps=window, forced=forced, capture_logits=n)
-    engine.set_option(_lib.OPT_PREFILL_GEMM, 1)  # the default
-    res = engine.infer(ids, bert, prompt, **kw)
-    worst, agree, total = _compare_logits(res, g, window, n)
     try:
+        engine.set_option(_lib.OPT_PREFILL_GEMM, gemm)
+        res = engine.infer(ids, bert, prompt, **kw)
+        worst, agree, total = _compare_logits(res, g, window, n)
         engine.set_option(_lib.OPT_PREFILL_GEMM, 0)
         ref = engine.infer(ids, bert, prompt, **kw)
     finally:
         engine.set_option(_lib.OPT_PREFILL_GEMM, 1)
     d = float(np.nanmax(np.abs(res.logits.cpu().numpy()[:, :, :1024] - ref.logits.cpu().numpy()[:, :, :1024])))
-    print(f"tcgen05 prefill {case}: max |dlogit| vs reference = {worst:.4f}, vs warp-MMA prefill = {d:.4f}, greedy {agree}/{total}")
+    print(f"tcgen05 prefill (gemm {gemm}) {case}: max |dlogit| vs reference = {worst:.4f}, vs warp-MMA prefill = {d:.4f}, greedy {agree}/{total}")
     assert worst <= LOGIT_TOL and agree == total
     assert d <= LOGIT_TOL
 
