@@ -81,7 +81,8 @@ SWEEP = ["cfg1_b1", "cfg4_b8", "cfg4_b64", "cfg4_b256", "cfg5_b128"]
 # (greedy, as SURVEY.md 8d prescribes for this config: the tokens - and with them the total work - do not depend on how the
 #  utterances are sharded; measured on B200 with this head: 122 tokens per utterance on average, 2..426)
 CFG3 = dict(total=120, lo=60, hi=140, prompt=150, top_k=1, top_p=1.0, temperature=1.0, repetition_penalty=1.35,
-            cap=1000, eos_window=1, eos_scale=1.4, weight_seed=3)
+            cap=1000, eos_window=1, eos_scale=1.4, weight_seed=3,
+            slots=56, slice_steps=24, admit_min=8)  # the continuous-batching schedule (StreamingSession)
 
 
 def workload_inputs(w, rank):
@@ -358,31 +359,55 @@ def cfg3_strong(dev, rank, world, barrier):
     prompt = prompt.to(dev)
     mine_count = [0]
 
-    def infer_fn(indices):
+    def infer_chunked(indices):
+        """one t2s_generate call: chunks of <= 56 utterances, each decoded in lock-step until its LAST sequence retires"""
         mine_count[0] = len(indices)
         r = eng.infer([ids[i] for i in indices], [bert[i] for i in indices], prompt[indices], top_k=c["top_k"], top_p=c["top_p"],
                       temperature=c["temperature"], repetition_penalty=c["repetition_penalty"], early_stop_num=c["cap"],
                       eos_suppress_steps=c["eos_window"], max_steps=1500, seed=77, utt_ids=list(indices))
         return r.sequences(), r.idx
 
-    shard.sharded_infer(infer_fn, L, rank=rank, world=world)  # warm-up
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    y_list, idx_list = shard.sharded_infer(infer_fn, L, rank=rank, world=world)
-    e1.record()
-    barrier()
-    ms = max(e0.elapsed_time(e1), 0.0)
-    wall = 1000.0 * (time.perf_counter() - t0)
+    def infer_continuous(indices):
+        """continuous batching: ONE resident session of <= 56 slots; a retired utterance's slot (and K/V pages) goes to the next
+        waiting utterance, so the long utterances of the whole share decode side by side instead of chunk after chunk"""
+        mine_count[0] = len(indices)
+        sess = gsb.StreamingSession(eng, slots=min(c["slots"], len(indices)), positions=c["hi"] + c["prompt"] + c["cap"] + 8,
+                                    slice_steps=c["slice_steps"], admit_min=c["admit_min"], top_k=c["top_k"], top_p=c["top_p"],
+                                    temperature=c["temperature"], repetition_penalty=c["repetition_penalty"], early_stop_num=c["cap"],
+                                    eos_suppress_steps=c["eos_window"], max_steps=1500, seed=77)
+        for i in indices:  # keys = submission order = position in `indices`
+            sess.submit([ids[i]], [bert[i]], prompt[i:i + 1])
+        ys, ks = [None] * len(indices), [0] * len(indices)
+        for key, toks, k in sess:
+            ys[key], ks[key] = toks, int(k)
+        return ys, ks
+
+    def digest_of(y_list):
+        import hashlib
+        return hashlib.sha1(b"".join(np.asarray(y, dtype=np.int64).tobytes() for y in y_list)).hexdigest()[:16]
+
+    def timed(fn):
+        shard.sharded_infer(fn, L, rank=rank, world=world)  # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        y_list, idx_list = shard.sharded_infer(fn, L, rank=rank, world=world)
+        e1.record()
+        barrier()
+        return max(e0.elapsed_time(e1), 0.0), 1000.0 * (time.perf_counter() - t0), y_list, idx_list
+
+    ms_ch, wall_ch, y_ch, idx_ch = timed(infer_chunked)
+    st0 = eng.stats()
+    ms, wall, y_list, idx_list = timed(infer_continuous)
     st = eng.stats()
-    my_ms = st["prefill_ms"] + st["decode_ms"]
+    my_ms = (st["prefill_ms"] + st["decode_ms"]) - (st0["prefill_ms"] + st0["decode_ms"]) if st["decode_ms"] >= st0["decode_ms"] else st["prefill_ms"] + st["decode_ms"]
     eng.close()
     parts = shard.partition_utterances(L, world)
     toks_by_rank = [sum(idx_list[i] for i in p) for p in parts]
-    import hashlib
-    digest = hashlib.sha1(b"".join(np.asarray(y, dtype=np.int64).tobytes() for y in y_list)).hexdigest()[:16]
-    return {"ms": ms, "wall_ms": wall, "tokens": int(sum(idx_list)), "digest": digest, "idx_mean": float(np.mean(idx_list)), "idx_max": int(max(idx_list)),
+    digest = digest_of(y_list)
+    same = sum(1 for a, b in zip(y_list, y_ch) if len(a) == len(b) and bool((np.asarray(a) == np.asarray(b)).all()))
+    return {"ms": ms, "wall_ms": wall, "chunked_ms": ms_ch, "chunked_digest": digest_of(y_ch), "chunked_tokens": int(sum(idx_ch)), "same_utts": same, "tokens": int(sum(idx_list)), "digest": digest, "idx_mean": float(np.mean(idx_list)), "idx_max": int(max(idx_list)),
             "idx_min": int(min(idx_list)), "utterances_per_rank": [len(p) for p in parts], "tokens_per_rank": toks_by_rank,
             "my_engine_ms": my_ms, "my_utterances": mine_count[0]}
 
@@ -517,24 +542,34 @@ def main():
     if not args.no_cfg3:
         try:
             c3 = cfg3_strong(dev, rank, world, barrier)
-            t3 = torch.tensor([c3["ms"], c3["my_engine_ms"]], device=dev, dtype=torch.float64)
+            t3 = torch.tensor([c3["ms"], c3["my_engine_ms"], c3["chunked_ms"]], device=dev, dtype=torch.float64)
             tmax, tmin = t3.clone(), t3.clone()
             if world > 1:
                 dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
                 dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-            job_ms = float(tmax[0])
+            job_ms, chunked_ms = float(tmax[0]), float(tmax[2])
             cfg3 = {
                 "workload": f"cfg3: {CFG3['total']} ragged utterances ({CFG3['lo']}..{CFG3['hi']} phonemes + {CFG3['prompt']} prompt tokens), "
                             f"natural EOS (EOS row of the head x{CFG3['eos_scale']}, weight seed {CFG3['weight_seed']}), greedy top_k={CFG3['top_k']} "
                             f"rp={CFG3['repetition_penalty']}, on-device retirement; FIXED total work sharded by shard.sharded_infer",
                 "scaling": "strong", "n_gpus": world, "tokens": c3["tokens"], "tokens_sha1": c3["digest"], "job_ms": job_ms,
                 "tokens_per_s": c3["tokens"] / (job_ms / 1000.0),
+                "schedule": f"continuous batching (StreamingSession: one resident session of <= {CFG3['slots']} slots per GPU, slices of "
+                            f"{CFG3['slice_steps']} steps, retired slots re-admitted {CFG3['admit_min']} at a time)",
+                "chunked": {"job_ms": chunked_ms, "tokens_per_s": c3["chunked_tokens"] / (chunked_ms / 1000.0), "tokens_sha1": c3["chunked_digest"],
+                            "schedule": "one t2s_generate call per GPU: chunks of <= 56 utterances, each decoded until its last sequence retires",
+                            "utterances_with_the_same_tokens_as_continuous": f"{c3['same_utts']}/{CFG3['total']}",
+                            "note": "greedy decoding of RANDOM-INIT weights (near-flat logits): which warp merges which K/V pages of a "
+                                    "sequence depends on the other sequences in its cluster, i.e. the fp32 summation order of the "
+                                    "attention merge depends on the batch composition, and a 1-ulp difference flips near-ties; the "
+                                    "same holds between either schedule and a batch-1 run (scripts/check_cb.py)"},
                 "tokens_per_utterance": {"mean": c3["idx_mean"], "min": c3["idx_min"], "max": c3["idx_max"]},
                 "utterances_per_rank": c3["utterances_per_rank"], "tokens_per_rank": c3["tokens_per_rank"],
                 "engine_ms_slowest_rank": float(tmax[1]), "engine_ms_fastest_rank": float(tmin[1]),
-                "limiter": "the job ends with its LONGEST utterance: every rank decodes in lock-step until its last sequence "
-                           "retires, so time ~ max over ranks of the longest utterance's steps x step time, while the per-GPU "
-                           "batch shrinks to total/N (15 at N=8) where a step costs about as much as at batch 32 (latency-bound chain)",
+                "limiter": "the job cannot end before its LONGEST utterance (its steps x the step time of a nearly empty batch: the "
+                           "latency-bound chain costs about as much at batch 5 as at batch 32); continuous batching removes the "
+                           "chunk-after-chunk serialisation at N <= 2 (> 56 utterances per GPU), at N >= 4 a GPU's share fits one "
+                           "session and both schedules coincide",
             }
         except Exception as ex:
             cfg3 = {"error": str(ex)[:300]}

@@ -72,13 +72,16 @@ class StreamingSession:
     session serves any number of utterances.  Utterances never interact and every Philox stream is keyed by (seed, key, own step),
     so an utterance gets the same tokens whatever slot it lands in and whenever it is admitted."""
 
-    def __init__(self, engine: T2SEngine, slots: int = 32, positions: int = 0, slice_steps: int = 25, top_k: int = 15,
+    def __init__(self, engine: T2SEngine, slots: int = 32, positions: int = 0, slice_steps: int = 25, admit_min: int = 1, top_k: int = 15,
                  top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, early_stop_num: int = -1,
                  eos_suppress_steps: int = EOS_WINDOW_BATCH, max_steps: int = MAX_STEPS, seed: Optional[int] = None,
                  forced: Optional[torch.Tensor] = None, capture_logits: int = 0):
         if slots < 1 or slice_steps < 1:
             raise ValueError("slots and slice_steps must be >= 1")
         self.eng, self.slots, self.positions, self.slice_steps = engine, int(slots), int(positions), int(slice_steps)
+        # an admission is a prefill (launch-bound for a handful of rows: ~2 ms): waiting utterances are taken in once at least
+        # `admit_min` slots are free (or as many as are waiting, or nothing is decoding), not one by one
+        self.admit_min = max(1, int(admit_min))
         self.kw = dict(top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
                        early_stop_num=early_stop_num, eos_suppress_steps=eos_suppress_steps, max_steps=max_steps, seed=seed)
         self.hooks = dict(forced=forced, capture_logits=capture_logits)
@@ -113,7 +116,10 @@ class StreamingSession:
 
     def _admit_waiting(self) -> None:
         while self.waiting and len(self.slot_key) < self.slots:
-            got = self._take(self.slots - len(self.slot_key))
+            free = self.slots - len(self.slot_key)
+            if self.slot_key and free < min(self.admit_min, len(self.waiting)):
+                break
+            got = self._take(free)
             if got is None:
                 break
             keys, ids, bert, prompt = got

@@ -585,7 +585,10 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     e->h_slot_local[slot] = b;
   }
   {
-    const size_t pages = admit ? e->next_page : std::max(e->next_page, (size_t)(cap > B ? (size_t)cap * max_pages : 0));
+    // a session opened with a reservation keeps max_pages per slot for EVERY slot - also when the first request fills all of them:
+    // a recycled slot may take an utterance that is longer than its previous occupant
+    const bool reserved = e->session_slots > 0 || e->session_positions > 0;
+    const size_t pages = admit ? e->next_page : std::max(e->next_page, (size_t)(reserved ? (size_t)cap * max_pages : 0));
     if (pages > e->pool_pages) {
       if (admit) return fail("t2s_admit: K/V pool exhausted (%zu pages needed, %zu reserved)", pages, e->pool_pages);
       const size_t bytes = (size_t)e->cfg.n_layer * pages * KV_PAGE_STRIDE * 2;  // K and V interleaved per (page, head)
@@ -1115,8 +1118,14 @@ extern "C" int t2s_generate(t2s_engine* e, const t2s_request* rq, int64_t* token
   acc.prefill_ms = 0; acc.decode_ms = 0; acc.decode_steps = 0; acc.decode_tokens = 0; acc.decode_kv_positions = 0; acc.prefill_rows = 0;
   int rc = 0;
   int64_t id_off = 0;
+  // t2s_set_utterance_ids covers the whole request: every chunk gets its own slice
+  const std::vector<int> all_uids = e->pending_uids;
+  e->pending_uids.clear();
+  if (!all_uids.empty() && (int)all_uids.size() != B)
+    return fail("t2s_generate: t2s_set_utterance_ids gave %zu ids for a batch of %d", all_uids.size(), B);
   for (int b0 = 0; b0 < B && !rc; b0 += per) {
     const int n = std::min(per, B - b0);
+    if (!all_uids.empty()) e->pending_uids.assign(all_uids.begin() + b0, all_uids.begin() + b0 + n);
     t2s_request sub = *rq;
     sub.batch = n;
     sub.phoneme_ids = rq->phoneme_ids + id_off;

@@ -489,3 +489,22 @@ def test_utterance_ids_make_sampling_independent_of_batching(engine, golden_dir)
     for b in range(2):
         assert torch.equal(part.sequences()[b], whole.sequences()[2 + b])
     assert not all(torch.equal(other.sequences()[b], whole.sequences()[2 + b]) for b in range(2))
+
+
+def test_utterance_ids_cover_a_chunked_call(engine, golden_dir):
+    """A call with more utterances than one decode launch holds (t2s_generate runs it in chunks) takes ONE list of utterance ids
+    for the whole call: every chunk gets its slice, so utterance 58 of a 60-utterance call samples exactly like the same utterance
+    in a call of its own with the same id (bench.py's config-3 job on one GPU is such a call)."""
+    g = _golden(golden_dir, "batch_b4")
+    ids, bert, prompt = _inputs(g)
+    n = 60
+    big_ids = [ids[i % 4] for i in range(n)]
+    big_bert = [bert[i % 4] for i in range(n)]
+    big_prompt = prompt[[i % 4 for i in range(n)]]
+    kw = dict(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=12, eos_suppress_steps=1, seed=99)
+    whole = engine.infer(big_ids, big_bert, big_prompt, utt_ids=list(range(500, 500 + n)), **kw)
+    assert len(whole.idx) == n
+    for j in (0, 31, 58):
+        one = engine.infer([big_ids[j]], [big_bert[j]], big_prompt[j:j + 1], utt_ids=[500 + j], **kw)
+        assert one.idx[0] == whole.idx[j]
+        assert torch.equal(one.sequences()[0], whole.sequences()[j])
