@@ -442,6 +442,9 @@ static void launch_decode_step(t2s_engine* e, const Ctx& c, cudaStream_t s) {
 // Large-batch decode step: projections on the tensor cores (k_gemm_tc<64>, LayerNorm folded into the epilogue,
 // A operand = the bf16 activations the previous kernel's epilogue wrote, fetched by TMA), attention / head /
 // sampler / plan as phase kernels.  Captured into a CUDA graph by t2s_decode.
+// (Round 2 also ran the step as a 256-row "prefill" - k_ln_rows + the persistent k_gemm_tcp<128> with the three prefill epilogues, 7
+// launches per layer: parity green and SLOWER, 1702 / 1958 / 2714 us per step at batch 64 / 128 / 256 against 1598 / 1917 / 2403 for this
+// form: at M <= 256 every projection is a fixed ~10-15 us latency chain whatever the kernel; removed.)
 static bool launch_decode_step_tc(t2s_engine* e, const Ctx& c, cudaStream_t s) {
   const int g = e->num_sms, B0 = c.B0;
   float* x0r = e->x0_rows.as<float>();
@@ -614,8 +617,10 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   int rc = 0;
   rc |= e->ints.ensure(n_ints * 4);
   rc |= e->kvoff.ensure(R * 8);
-  rc |= e->x0_rows.ensure((size_t)T * D * 4);
-  rc |= e->x0b_rows.ensure((size_t)T * D * 2);
+  // scratch rows that the large-batch decode graph (mode 3) points at directly: a reallocation invalidates the captured graph
+  void* const scratch_before[4] = {e->x0_rows.p, e->x0b_rows.p, e->xf.p, e->xb.p};
+  rc |= e->x0_rows.ensure(R * D * 4);
+  rc |= e->x0b_rows.ensure(R * D * 2);
   rc |= e->yb1.ensure(R * D * 2);
   rc |= e->yb2.ensure(R * D * 2);
   rc |= e->sp1.ensure(R * 32 * 8);
@@ -627,7 +632,13 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
   rc |= e->y2.ensure(R * D * 4);
   rc |= e->stat2.ensure(R * 8);
   rc |= e->bert_rows.ensure((size_t)n_text * BERT * 2);
-  if (e->prefill_gemm) { rc |= e->xf.ensure((size_t)T * D * 4); rc |= e->xb.ensure((size_t)T * D * 2); }
+  rc |= e->xf.ensure((e->prefill_gemm ? R : (size_t)MAX_B) * D * 4);
+  rc |= e->xb.ensure((e->prefill_gemm ? R : (size_t)MAX_B) * D * 2);
+  if (e->graph_exec && (scratch_before[0] != e->x0_rows.p || scratch_before[1] != e->x0b_rows.p || scratch_before[2] != e->xf.p ||
+                        scratch_before[3] != e->xb.p)) {
+    cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+  }
   if (!admit) {  // session buffers (a resident session's must not move)
     rc |= e->ints2.ensure((size_t)(MAX_B * 7 + 16) * 4);
     rc |= e->gen.ensure((size_t)cap * rq->max_steps * 4);

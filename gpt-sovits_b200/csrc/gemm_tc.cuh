@@ -336,6 +336,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / TC_BK;
+  if (ep.n_rows) M = min(M, __ldcg(ep.n_rows));  // large-batch decode: the live row count is a device value (same in every thread)
   const int n_tiles_n = N / BN, n_tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles_n;
   // tile t = (row tile t / n_tiles_n, column tile t % n_tiles_n): CTAs that run side by side share the rows of A through L2
 

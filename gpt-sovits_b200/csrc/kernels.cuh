@@ -558,7 +558,7 @@ __global__ void k_rows_stats(const float* __restrict__ y, const int* __restrict_
                              float2* __restrict__ sp) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
-  const int r = rows[i];
+  const int r = rows ? rows[i] : i;
   const float* src = y + (size_t)r * D + lane * 16;  // lane = 16-feature tile
   float s = 0.f, q = 0.f;
 #pragma unroll
