@@ -64,6 +64,7 @@ struct TcEpilogue {
   const float* be;
   const float* b2;         // EPI_D_FFN2: linear2.bias
   int dbg;                 // measurement only (scripts/mb_gemm.cu): 1 = no global stores, 2 = no staging either, 4 = no prefetch loads
+  long long* tl;           // measurement only: clock64 stamps of k_gemm_tcp, [CTA][tile < 8][8] (scripts/mb_gemm.cu)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -289,10 +290,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 //     block through shared memory so that global reads (residual) and writes are 128-byte row segments instead of one 64-byte piece
 //     per thread and row (the non-persistent kernel's epilogue was LSU-bound: 32 different lines per store instruction); the
 //     loads of a block (bias, residual) are requested one block ahead.
-// Measured (scripts/mb_gemm.cu): the main loop alone runs at 1.25-1.4 PFLOP/s; with the epilogue's stores the
-// projections are bound by the write path (L2 / HBM), not by the tensor pipe or the operand stream.  A weight-stationary
-// variant (a CTA keeps one 128-column block of W in shared memory and streams only A) was built and measured SLOWER (0.81-0.84
-// PFLOP/s main loop: N = 128 MMAs are shared-memory-bandwidth bound) and removed.
+// Measured (scripts/mb_gemm.cu): the main loop alone runs at 1.25-1.4 PFLOP/s (2.1 us per K = 512 tile); with the
+// epilogue a tile takes ~7 us: SHARED MEMORY is the shared resource - per 128 x 256 tile 393 KB of TMA fill + 393 KB of operand
+// reads by the MMAs + 2 x 128 KB of staging = 1.04 MB against 128 B/clk, a 4.1 us floor - so the K = 512 projections run at
+// 0.45-0.75 PFLOP/s and only linear2 (K = 2048) reaches 1 PFLOP/s.  Built, measured and removed: a weight-stationary variant (a
+// CTA keeps one 128-column block of W in shared memory and streams only A: 0.81-0.84 PFLOP/s main loop, N = 128 MMAs read 128 B
+// of operands per clock, the whole shared-memory bandwidth); eight epilogue warps instead of four (no change); drain warps
+// (TMEM -> staging) and store warps (staging -> global) as separate roles with double-buffered staging (no change: the stores
+// alone sustain 21-26 B/clk per SM, scripts/mb_store.cu); bulk-copy stores from the staging block (slower).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2.. epilogue (TMEM lane quarter = warp % 4).
 // Epilogues: EPI_QKV, EPI_RESID, EPI_RELU (the three of T2SBlock.process_prompt, t2s_model.py:135-174).
 constexpr int TCP_EPI_WARPS = 4, TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;  // 8 (two per lane quarter) measured: no faster, and 204 registers spill
@@ -356,10 +361,11 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: k-block counter `it` runs over all tiles of this CTA =====
-      unsigned it = 0;
+      unsigned it = 0, lt = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x) {
+      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, ++lt) {
         const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
+        if (ep.tl && lt < 8) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 0] = clock64();
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const unsigned s = it % NST, ph = (it / NST) & 1u;
           if (!mbar_wait(empty0 + 8 * s, ph ^ 1u, ep.error_flag)) { ok = false; break; }
@@ -368,6 +374,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           tma_load_2d(sa, &map_a, kb * TC_BK, m0, full0 + 8 * s);
           tma_load_2d(sa + CF::A_BYTES, &map_w, kb * TC_BK, n0, full0 + 8 * s);
         }
+        if (ep.tl && lt < 8) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 1] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -378,10 +385,12 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         const unsigned acc = lt & 1u, aph = (lt >> 1) & 1u;
         if (!mbar_wait(acce0 + 8 * acc, aph ^ 1u, ep.error_flag)) break;  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ep.tl && lt < 8) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 2] = clock64();
         const uint32_t tacc = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const unsigned s = it % NST, ph = (it / NST) & 1u;
           if (!mbar_wait(full0 + 8 * s, ph, ep.error_flag)) { ok = false; break; }
+          if (ep.tl && lt < 8 && kb == 0) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 3] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * CF::STAGE_BYTES), sb = sa + CF::A_BYTES;
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
@@ -390,6 +399,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           umma_commit(empty0 + 8 * s);
         }
         if (ok) umma_commit(accf0 + 8 * acc);
+        if (ep.tl && lt < 8) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 4] = clock64();
       }
     }
   } else {  // ===== epilogue warps: TMEM lane quarter warp % 4, column share (warp - 2) / 4 =====
@@ -428,6 +438,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       if (ep.mode == EPI_QKV && n0 >= D && row_t < M) kvo = ep.kvoff[row_t];
       if (!mbar_wait(accf0 + 8 * acc, aph, ep.error_flag)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (ep.tl && lt < 8 && warp == 2 && lane == 0) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c0 = ch * CW; c0 < (ch + 1) * CW; c0 += 32) {
@@ -440,6 +451,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(acce0 + 8 * acc);
+          if (ep.tl && lt < 8 && warp == 2 && lane == 0) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 6] = clock64();
         }
         float4 rn[8], bAn = bA, bBn = bB;  // next block's loads, in flight during this block's staging and stores
         const bool more = !last || t + (int)gridDim.x < n_tiles;
@@ -494,6 +506,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           for (int i = 0; i < 8; ++i) rs[i] = rn[i];
         }
       }
+      if (ep.tl && lt < 8 && warp == 2 && lane == 0) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 7] = clock64();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }

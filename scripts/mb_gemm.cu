@@ -48,9 +48,11 @@ struct Bufs {
 };
 
 static int g_dbg = 0;
+static long long* g_tl = nullptr;
 static bool run(int variant, int mode, const Bufs& b, int M, int N, int K, int num_sms, cudaStream_t s) {
   TcEpilogue ep{};
   ep.dbg = g_dbg;
+  ep.tl = (variant == 1) ? g_tl : nullptr;
   ep.mode = mode; ep.bias = b.bias; ep.error_flag = b.err;
   const int o = variant ? 1 : 0;
   if (mode == EPI_QKV) { ep.out_f32 = b.outf[o]; ep.kpool = b.pool[o]; ep.vpool = b.pool[o] + KV_V_OFF; ep.kvoff = b.kvoff; ep.layer_off = 0; }
@@ -74,6 +76,8 @@ int main(int argc, char** argv) {
       {"qkv  (N=1536,K=512)", EPI_QKV, 3 * D, D}, {"wo   (N=512,K=512)", EPI_RESID, D, D},
       {"w1   (N=2048,K=512)", EPI_RELU, FF, D}, {"w2   (N=512,K=2048)", EPI_RESID, D, FF}};
   int fails = 0;
+  const bool want_tl = argc > 4 && atoi(argv[4]) != 0;  // print the pipeline timeline of CTAs 0 and 100 of k_gemm_tcp<256>
+  if (want_tl) { CK(cudaMalloc(&g_tl, (size_t)148 * 64 * 8)); }
   for (int mi = 0; mi < 2; ++mi) {
     const int M = Ms[mi];
     if (only_m && only_m != M) continue;
@@ -117,6 +121,22 @@ int main(int argc, char** argv) {
         CK(cudaStreamSynchronize(s));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         ms_v[variant] = ms / reps;
+        if (want_tl && variant == 1) {
+          CK(cudaMemset(g_tl, 0, (size_t)148 * 64 * 8));
+          run(variant, sh.mode, b, M, sh.N, sh.K, num_sms, s);
+          CK(cudaStreamSynchronize(s));
+          std::vector<long long> h((size_t)148 * 64);
+          CK(cudaMemcpy(h.data(), g_tl, h.size() * 8, cudaMemcpyDeviceToHost));
+          for (int cta : {0, 100}) {
+            const long long t0 = h[(size_t)cta * 64];
+            printf("  timeline CTA %d of %s (us after the producer's first stamp; per tile: producer start | producer done | MMA acc free | first operands | MMAs issued | epilogue start | acc released | epilogue done)\n", cta, sh.name);
+            for (int lt = 0; lt < 8 && h[(size_t)cta * 64 + lt * 8]; ++lt) {
+              printf("    tile %d:", lt);
+              for (int k = 0; k < 8; ++k) printf(" %7.2f", (h[(size_t)cta * 64 + lt * 8 + k] - t0) / 1965.0);
+              printf("\n");
+            }
+          }
+        }
         int herr = 0; CK(cudaMemcpy(&herr, b.err, 4, cudaMemcpyDeviceToHost));
         if (herr) { printf("  variant %d: WATCHDOG error flag set\n", variant); ++fails; CK(cudaMemset(b.err, 0, 4)); }
         if (variant > 0) {  // bitwise against variant 0
