@@ -284,3 +284,74 @@ def test_bucket_batches_matches_reference_to_batch(golden_dir):
         gsb.bucket_batches([1, 2], 0)
     with pytest.raises(ValueError):
         gsb.recovery_order([[1]], [[0, 1]])
+
+
+def test_streaming_session_admission_policy():
+    """StreamingSession's host logic with a fake engine (no GPU): every utterance is served exactly once, at most `slots` decode
+    at the same time, released slots are reused, and with admit_min = n waiting utterances are admitted in groups of >= n (or all
+    that wait) instead of one prefill per freed slot."""
+    import gpt_sovits_b200 as gsb
+
+    class FakeResult:
+        def __init__(self, toks, idx):
+            self._t, self.idx, self.logits = toks, idx, None
+
+        def sequences(self):
+            return self._t
+
+    class FakeEngine:
+        """utterance k needs 3 + 2 * (k % 5) steps; tokens = [k] * steps"""
+        def __init__(self):
+            self.slot_utt, self.slot_left, self.free, self.admissions, self.max_active = {}, {}, [], [], 0
+
+        def _place(self, keys, slots):
+            for k, s in zip(keys, slots):
+                self.slot_utt[s], self.slot_left[s] = k, 3 + 2 * (k % 5)
+            self.admissions.append(len(keys))
+            self.max_active = max(self.max_active, sum(1 for v in self.slot_left.values() if v > 0))
+
+        def infer(self, ids, bert, prompt, max_new_steps=0, reserve_slots=0, reserve_positions=0, utt_ids=None, **kw):
+            self.cap = reserve_slots
+            self._place(list(utt_ids), list(range(len(ids))))
+            return FakeResult(None, None)
+
+        def admit(self, ids, bert, prompt, utt_ids=None):
+            slots = []
+            for _ in ids:
+                slots.append(self.free.pop(0) if self.free else len(self.slot_utt))
+                assert slots[-1] < self.cap
+            self._place(list(utt_ids), slots)
+            return slots
+
+        def session_result(self):
+            n = max(self.slot_utt) + 1
+            toks = [torch.full((3 + 2 * (self.slot_utt.get(s, 0) % 5),), self.slot_utt.get(s, 0), dtype=torch.int64) for s in range(n)]
+            return FakeResult(toks, [(3 + 2 * (self.slot_utt[s] % 5)) if s in self.slot_utt and self.slot_left[s] <= 0 else -1 for s in range(n)])
+
+        def release(self, slots):
+            for s in slots:
+                self.slot_left[s] = 10 ** 9  # empty until re-admitted
+            self.free = sorted(set(self.free) | set(slots))
+
+        def decode_more(self, n):
+            for s in self.slot_left:
+                if self.slot_left[s] < 10 ** 8:
+                    self.slot_left[s] -= n
+
+    for admit_min in (1, 4):
+        eng = FakeEngine()
+        sess = gsb.StreamingSession(eng, slots=6, slice_steps=2, admit_min=admit_min, top_k=1)
+        n = 23
+        keys = sess.submit([torch.zeros(4, dtype=torch.int64)] * n, [torch.zeros(1024, 4)] * n, torch.zeros(n, 5, dtype=torch.int64))
+        assert keys == list(range(n))
+        got = {}
+        for key, toks, idx in sess:
+            assert key not in got
+            got[key] = (toks, idx)
+        assert sorted(got) == list(range(n))
+        for k, (toks, idx) in got.items():
+            assert idx == 3 + 2 * (k % 5) and bool((toks == k).all())
+        assert eng.max_active <= 6 and sum(eng.admissions) == n
+        if admit_min == 4:  # groups of >= 4 except the tail of the queue
+            assert all(a >= 4 for a in eng.admissions[:-1]), eng.admissions
+            assert len(eng.admissions) < n - 6
