@@ -78,6 +78,7 @@ struct t2s_engine {
   bool wide_ok = false;     // 144 CTAs of k_decode_wide can be co-resident
   DevBuf wrow_g, wrow_head, wrow_head_g, head_c;  // gamma-folded row-major copies (Wqkv, W1 per layer; head) + head c1/c0
   bool weights_final = false;
+  std::vector<CUtensorMap> tcp_wmaps;  // persistent prefill GEMM: the four weight maps of every layer (built on first use)
   float alpha_audio = 1.f, alpha_text = 1.f;
   std::vector<char> loaded;  // per (tensor, layer)
   // kv pool
@@ -344,6 +345,7 @@ extern "C" int t2s_load_tensor(t2s_engine* e, int32_t id, int32_t layer, const v
   if (!on_device) { CK(cudaStreamSynchronize(s)); tmp.release(); }
   e->loaded[(size_t)id * (e->cfg.n_layer + 1) + (per_layer ? layer : 0)] = 1;
   e->weights_final = false;
+  e->tcp_wmaps.clear();
   return 0;
 }
 
@@ -813,8 +815,25 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     // 1: persistent kernel (128 x 256 tiles, operand ring across tiles, two TMEM accumulators); 2: one 128 x 128 tile per CTA (round 1)
     const bool persistent = e->prefill_gemm == 1;
     const int T_ = T, nsm = e->num_sms;
-    auto gemm = [&](const bf16* A, const bf16* W, int N, int K, const TcEpilogue& ep) {
-      return persistent ? launch_gemm_tcp<256>(A, W, T_, N, K, ep, nsm, s) : launch_gemm_tc<128>(A, W, T_, N, K, ep, s);
+    // tensor maps of the persistent kernel: weights once per engine, activations (xb, attn: [T, 512]; h: [T, 2048]) once per call
+    CUtensorMap map_xb, map_attn, map_h;
+    if (persistent) {
+      if (e->tcp_wmaps.empty()) {
+        e->tcp_wmaps.resize((size_t)4 * cp.n_layer);
+        for (int l = 0; l < cp.n_layer && ok; ++l) {
+          const bf16* wr = e->wrow.as<bf16>() + (size_t)l * LW;
+          ok = ok && make_tmap_bf16(&e->tcp_wmaps[4 * l + 0], wr + OFF_WQKV, 3 * D, D, 256) && make_tmap_bf16(&e->tcp_wmaps[4 * l + 1], wr + OFF_WO, D, D, 256) &&
+               make_tmap_bf16(&e->tcp_wmaps[4 * l + 2], wr + OFF_W1, FF, D, 256) && make_tmap_bf16(&e->tcp_wmaps[4 * l + 3], wr + OFF_W2, D, FF, 256);
+        }
+        if (!ok) e->tcp_wmaps.clear();
+      }
+      ok = ok && make_tmap_bf16(&map_xb, xb, (uint64_t)T, D, TC_BM) && make_tmap_bf16(&map_attn, cp.attn, (uint64_t)T, D, TC_BM) &&
+           make_tmap_bf16(&map_h, cp.h, (uint64_t)T, FF, TC_BM);
+    }
+    auto gemm = [&](const bf16* A, const bf16* W, int N, int K, const TcEpilogue& ep, const CUtensorMap* ma, int layer, int which) {
+      if (!persistent) return launch_gemm_tc<128>(A, W, T_, N, K, ep, s);
+      launch_gemm_tcp_maps<256>(*ma, e->tcp_wmaps[(size_t)4 * layer + which], T_, N, K, ep, nsm, s);
+      return true;
     };
     for (int l = 0; l < cp.n_layer && ok; ++l) {
       const float* vl = cp.wvec + (size_t)l * LV;
@@ -832,17 +851,17 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_QKV; ep.bias = vl + VO_BQKV; ep.out_f32 = cp.q; ep.kpool = cp.kpool; ep.vpool = cp.vpool;
       ep.kvoff = cp.row_kvoff; ep.layer_off = (size_t)l * cp.kv_layer_stride;
-      ok = ok && gemm(xb, wr + OFF_WQKV, 3 * D, D, ep);
+      ok = ok && gemm(xb, wr + OFF_WQKV, 3 * D, D, ep, &map_xb, l, 0);
       k_prefill_attn_tc<<<dim3(e->n_qtiles, NH), 128, 0, s>>>(cp, l, e->d_qtiles, d_text_len_by_slot);
       ep = TcEpilogue{};
       ep.error_flag = cp.abort_flag;
       ep.mode = EPI_RESID; ep.bias = vl + VO_BO; ep.resid = resid; ep.out_f32 = cp.y1;
-      ok = ok && gemm(cp.attn, wr + OFF_WO, D, D, ep);
+      ok = ok && gemm(cp.attn, wr + OFF_WO, D, D, ep, &map_attn, l, 1);
       k_ln_rows<<<ln_blocks, 256, 0, s>>>(cp.y1, vl + VO_G1, vl + VO_BE1, xf, xb, T, 1);
       ep.mode = EPI_RELU; ep.bias = vl + VO_B1; ep.resid = nullptr; ep.out_f32 = nullptr; ep.out_b16 = cp.h;
-      ok = ok && gemm(xb, wr + OFF_W1, FF, D, ep);
+      ok = ok && gemm(xb, wr + OFF_W1, FF, D, ep, &map_xb, l, 2);
       ep.mode = EPI_RESID; ep.bias = vl + VO_B2; ep.resid = xf; ep.out_f32 = cp.y2; ep.out_b16 = nullptr;
-      ok = ok && gemm(cp.h, wr + OFF_W2, D, FF, ep);
+      ok = ok && gemm(cp.h, wr + OFF_W2, D, FF, ep, &map_h, l, 3);
       e->launches += 7;
     }
     if (!ok) return fail("%s: cuTensorMapEncodeTiled failed", who);

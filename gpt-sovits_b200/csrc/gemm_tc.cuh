@@ -600,6 +600,15 @@ static inline bool launch_gemm_tc(const bf16* A, const bf16* W, int M, int N, in
   return true;
 }
 
+// persistent variant (prefill) with tensor maps the caller built once (the weight maps never change; an activation map changes only
+// with the row count): cuTensorMapEncodeTiled twice per projection is measurable when a prefill of a few hundred rows is launch-bound
+template <int BN>
+static inline void launch_gemm_tcp_maps(const CUtensorMap& ma, const CUtensorMap& mw, int M, int N, int K, const TcEpilogue& ep, int num_sms,
+                                        cudaStream_t s) {
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / BN);
+  k_gemm_tcp<BN><<<tiles < num_sms ? tiles : num_sms, TCP_THREADS, TcpCfg<BN>::SMEM_BYTES, s>>>(ma, mw, M, N, K, ep);
+}
+
 // persistent variant (prefill): grid = min(tiles, SMs), tiles of 128 x BN
 template <int BN>
 static inline bool launch_gemm_tcp(const bf16* A, const bf16* W, int M, int N, int K, const TcEpilogue& ep, int num_sms, cudaStream_t s) {
