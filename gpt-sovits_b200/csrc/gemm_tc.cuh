@@ -63,7 +63,7 @@ struct TcEpilogue {
   const float* g;          // EPI_D_O: previous norm2 gamma/beta; EPI_D_FFN2: this layer's norm1 gamma/beta
   const float* be;
   const float* b2;         // EPI_D_FFN2: linear2.bias
-  int dbg;                 // measurement only (scripts/mb_gemm.cu): 1 = no global stores, 2 = no staging either, 4 = no prefetch loads
+  int dbg;                 // measurement only (scripts/mb_gemm.cu): 1 = no global stores, 2 = no staging either, 4 = no prefetch loads, 8 = staged epilogue for every mode
   long long* tl;           // measurement only: clock64 stamps of k_gemm_tcp, [CTA][tile < 8][8] (scripts/mb_gemm.cu)
 };
 
@@ -322,6 +322,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 256-bit global stores (sm_100): one whole 32-byte sector per lane
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -427,7 +431,8 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
       }
     };
-    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, ch * CW, rs, bA, bB);
+    const bool staged = ep.mode == EPI_RESID || (ep.dbg & 8);  // dbg 8: every epilogue through the staging block (measurement)
+    if (staged && (int)blockIdx.x < n_tiles) prefetch(blockIdx.x, ch * CW, rs, bA, bB);
     unsigned lt = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
       const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
@@ -443,6 +448,11 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 #pragma unroll 1
       for (int c0 = ch * CW; c0 < (ch + 1) * CW; c0 += 32) {
         const int f0 = n0 + c0;
+        float4 bd[8];  // direct path: the block's 32 bias values (same address in every lane: one transaction each), requested
+        if (!staged) {  // in front of the TMEM load so that both latencies overlap
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bd[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + j);
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -452,6 +462,58 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(acce0 + 8 * acc);
           if (ep.tl && lt < 8 && warp == 2 && lane == 0) ep.tl[((size_t)blockIdx.x * 8 + lt) * 8 + 6] = clock64();
+        }
+        if (!staged) {
+          // ---- direct path (QKV, ReLU): the thread holds 32 consecutive columns of ITS row (128 B of fp32 / 64 B of bf16) and writes
+          // them itself with 256-bit stores, one whole sector per lane: 15 B/clk per SM (scripts/mb_store.cu) against 24 for the
+          // re-staged 128-byte segments, but no pass through shared memory, which the operand ring and the MMAs saturate
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bd[j];
+            x[4 * j] = __uint_as_float(v[4 * j]) + b.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          }
+          if ((ep.dbg & 1) || row_t >= M) {
+            // no stores for this lane (rows past M); the warp reconverges below before the next (warp-aligned) TMEM load
+          } else if (ep.mode == EPI_QKV && f0 < D) {
+            float* o = ep.out_f32 + (size_t)row_t * D + f0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_global_256(o + 8 * j, __float_as_uint(x[8 * j] * QSCALE), __float_as_uint(x[8 * j + 1] * QSCALE), __float_as_uint(x[8 * j + 2] * QSCALE),
+                            __float_as_uint(x[8 * j + 3] * QSCALE), __float_as_uint(x[8 * j + 4] * QSCALE), __float_as_uint(x[8 * j + 5] * QSCALE),
+                            __float_as_uint(x[8 * j + 6] * QSCALE), __float_as_uint(x[8 * j + 7] * QSCALE));
+          } else {
+            uint32_t pk[16];
+            if (ep.mode == EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf2(fmaxf(x[2 * j], 0.f), fmaxf(x[2 * j + 1], 0.f));
+              bf16* o = ep.out_b16 + (size_t)row_t * N + f0;
+              st_global_256(o, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+              st_global_256(o + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            } else {
+              // k or v: the 32 columns are one head row (64 B) of the K/V page; its 16-byte chunk c lives at position c ^ swz
+              // (common.cuh kv_feat), so position p holds chunk p ^ swz: bit 0 of swz swaps the chunks inside a 32-byte half, bit 1
+              // swaps the halves
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf2(x[2 * j], x[2 * j + 1]);
+              const int swz = kv_swz_of(kvo);
+              if (swz & 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { uint32_t tmp = pk[j]; pk[j] = pk[4 + j]; pk[4 + j] = tmp; tmp = pk[8 + j]; pk[8 + j] = pk[12 + j]; pk[12 + j] = tmp; }
+              }
+              if (swz & 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const uint32_t tmp = pk[j]; pk[j] = pk[8 + j]; pk[8 + j] = tmp; }
+              }
+              const int fk = f0 < 2 * D ? f0 - D : f0 - 2 * D;
+              bf16* o = (f0 < 2 * D ? ep.kpool : ep.vpool) + ep.layer_off + (size_t)kvo + (size_t)(fk >> 5) * KV_HEAD_STRIDE;
+              st_global_256(o, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+              st_global_256(o + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            }
+          }
+          __syncwarp();
+          continue;
         }
         float4 rn[8], bAn = bA, bBn = bB;  // next block's loads, in flight during this block's staging and stores
         const bool more = !last || t + (int)gridDim.x < n_tiles;
