@@ -140,8 +140,9 @@ class StreamingSession:
             if not self.slot_key:
                 return
             res = self.eng.session_result()
-            seqs = res.sequences()
             finished = [sl for sl in self.slot_key if res.idx[sl] >= 0]
+            if finished:
+                seqs = res.sequences()
             for sl in finished:
                 yield self.slot_key.pop(sl), seqs[sl].clone(), res.idx[sl]
             if finished:
