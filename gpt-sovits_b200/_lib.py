@@ -24,7 +24,7 @@ F32, F16, BF16 = 0, 1, 2
  W_NORM1_W, W_NORM1_B, W_NORM2_W, W_NORM2_B, W_COUNT) = range(21)
 
 OPT_DECODE_MODE, OPT_PREFILL_GEMM, OPT_NUM_CTAS, OPT_CHECK_STEPS, OPT_TC_DECODE_MIN_BATCH = 0, 1, 2, 3, 4
-OPT_SESSION_SLOTS, OPT_SESSION_POSITIONS = 5, 6
+OPT_SESSION_SLOTS, OPT_SESSION_POSITIONS, OPT_HOOKS_BY_UTTERANCE = 5, 6, 7
 
 EXPORTS = ["t2s_create", "t2s_destroy", "t2s_last_error", "t2s_load_tensor", "t2s_prefill", "t2s_admit", "t2s_release_slots", "t2s_set_utterance_ids", "t2s_decode",
            "t2s_result", "t2s_generate", "t2s_set_forced_tokens", "t2s_set_logits_capture",

@@ -75,7 +75,7 @@ class StreamingSession:
     def __init__(self, engine: T2SEngine, slots: int = 32, positions: int = 0, slice_steps: int = 25, admit_min: int = 1, top_k: int = 15,
                  top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, early_stop_num: int = -1,
                  eos_suppress_steps: int = EOS_WINDOW_BATCH, max_steps: int = MAX_STEPS, seed: Optional[int] = None,
-                 forced: Optional[torch.Tensor] = None, capture_logits: int = 0):
+                 forced: Optional[torch.Tensor] = None, capture_logits: int = 0, hooks_by_key: int = 0):
         if slots < 1 or slice_steps < 1:
             raise ValueError("slots and slice_steps must be >= 1")
         self.eng, self.slots, self.positions, self.slice_steps = engine, int(slots), int(positions), int(slice_steps)
@@ -84,7 +84,8 @@ class StreamingSession:
         self.admit_min = max(1, int(admit_min))
         self.kw = dict(top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
                        early_stop_num=early_stop_num, eos_suppress_steps=eos_suppress_steps, max_steps=max_steps, seed=seed)
-        self.hooks = dict(forced=forced, capture_logits=capture_logits)
+        # test hooks; hooks_by_key = n > 0: rows of `forced` / of the captured logits are indexed by utterance key (n keys), not by slot
+        self.hooks = dict(forced=forced, capture_logits=capture_logits, hooks_by_utterance=int(hooks_by_key))
         self.waiting: List[Tuple[int, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = []  # (key, ids, bert, prompt row)
         self.slot_key: Dict[int, int] = {}  # session slot -> key of the utterance decoding in it
         self.n_submitted = 0

@@ -135,6 +135,7 @@ struct Ctx {
   int n_forced;
   float* logits_rec;
   int n_logits_rec;
+  int hook_rows;  // 0: the two hooks above are indexed by session slot ([.][B0]); n > 0: by utterance id, n rows (T2S_OPT_HOOKS_BY_UTTERANCE)
   uint32_t* seen;  // [B0][SEEN_WORDS]
   // persistent-kernel grid barrier + watchdog, statistics
   unsigned* bar;

@@ -109,6 +109,7 @@ struct t2s_engine {
   int n_forced = 0;
   float* logits_rec = nullptr;
   int n_logits_rec = 0;
+  int hook_rows = 0;  // T2S_OPT_HOOKS_BY_UTTERANCE
   long long* timeline = nullptr;
   int tl_step = 0, tl_slots = 0;
   int decode_mode = 5, prefill_gemm = 0, num_ctas = 0, check_steps = 16, tc_decode_min_batch = 160;
@@ -403,6 +404,7 @@ extern "C" int t2s_set_option(t2s_engine* e, int32_t opt, int64_t v) {
     case T2S_OPT_NUM_CTAS: if (v != 0 && (v < MAX_B / 2 || v > 1024)) return fail("num_ctas must be 0 or in [128, 1024]"); e->num_ctas = (int)v; break;
     case T2S_OPT_TC_DECODE_MIN_BATCH: if (v < 0 || v > 100000) return fail("tc_decode_min_batch out of range"); e->tc_decode_min_batch = (int)v; break;
     case T2S_OPT_SESSION_SLOTS: if (v < 0 || v > MAX_B) return fail("session_slots must be in [0,%d]", MAX_B); e->session_slots = (int)v; break;
+    case T2S_OPT_HOOKS_BY_UTTERANCE: if (v < 0 || v > 1000000) return fail("hooks_by_utterance out of range"); e->hook_rows = (int)v; break;
     case T2S_OPT_SESSION_POSITIONS: if (v < 0 || v > 4000) return fail("session_positions must be in [0,4000]"); e->session_positions = (int)v; break;
     case T2S_OPT_CHECK_STEPS: if (v < 1 || v > 4096) return fail("check_steps out of range"); e->check_steps = (int)v; break;
     default: return fail("unknown option %d", opt);
@@ -757,6 +759,7 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     c.slot_base = e->slot_base;
     c.gen = e->gen.as<int>(); c.sampled = e->sampled.as<int>();
     c.forced = e->forced; c.n_forced = e->n_forced; c.logits_rec = e->logits_rec; c.n_logits_rec = e->n_logits_rec;
+    c.hook_rows = e->hook_rows;
     c.seen = e->seen.as<uint32_t>();
     c.timeline = e->timeline; c.tl_step = e->tl_step; c.tl_slots = e->tl_slots;
   }
@@ -803,7 +806,16 @@ static int prefill_impl(t2s_engine* e, const t2s_request* rq, cudaStream_t s, bo
     k_bert_rows<__half><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
   else
     k_bert_rows<bf16><<<n_text, 256, 0, s>>>(e->bert_rows.as<bf16>(), dptr, dsc, dst_, e->d_trow_slot, e->d_trow_j);
-  k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
+  if (e->prefill_gemm == 1) {
+    // bert_proj (t2s_model.py:613) on the persistent tcgen05 GEMM: [text rows, 1024] x [512, 1024]^T, added in place to the text
+    // rows of x0 (which hold embedding + bias + positional term) through the row map; the bf16 copy x0b is not read on this path
+    TcEpilogue ep{};
+    ep.error_flag = cp.abort_flag; ep.mode = EPI_RESID; ep.resid = cp.x0; ep.out_f32 = cp.x0; ep.row_map = e->d_trow_row;
+    if (!launch_gemm_tcp<256>(e->bert_rows.as<bf16>(), e->wrow.as<bf16>() + (size_t)e->cfg.n_layer * LW, n_text, D, BERT, ep, g, s))
+      return fail("%s: cuTensorMapEncodeTiled failed", who);
+  } else {
+    k_bert_proj<<<g, NT, SMEM_MAX, s>>>(cp, e->bert_rows.as<bf16>(), e->d_trow_row, n_text);
+  }
   e->launches += 4;
   const int* d_text_len_by_slot = e->slot_aux.as<int>();  // the attention kernels index text_len by session slot
   if (e->prefill_gemm) {

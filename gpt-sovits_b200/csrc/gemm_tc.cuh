@@ -64,6 +64,7 @@ struct TcEpilogue {
   const float* be;
   const float* b2;         // EPI_D_FFN2: linear2.bias
   int dbg;                 // measurement only (scripts/mb_gemm.cu): 1 = no global stores, 2 = no staging either, 4 = no prefetch loads, 8 = staged epilogue for every mode
+  const int* row_map;      // k_gemm_tcp, EPI_RESID: GEMM row r reads its residual from / writes its result to row row_map[r] (NULL: r)
   long long* tl;           // measurement only: clock64 stamps of k_gemm_tcp, [CTA][tile < 8][8] (scripts/mb_gemm.cu)
 };
 
@@ -421,13 +422,15 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       const int m0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * BN;
       const int f0 = n0 + c0, rbase = m0 + wq * 32;
       const bool f32map = ep.mode == EPI_RESID || (ep.mode == EPI_QKV && f0 < D);
-      if (f32map) { b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + c4); b1 = b0; }
+      if (!ep.bias) { b0 = make_float4(0.f, 0.f, 0.f, 0.f); b1 = b0; }
+      else if (f32map) { b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + c4); b1 = b0; }
       else { b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + 2 * c8); b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + f0) + 2 * c8 + 1); }
       if (ep.mode == EPI_RESID) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = rbase + r4 + 4 * i;
-          r[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(ep.resid + (size_t)row * N + f0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int grow = (ep.row_map && row < M) ? __ldg(ep.row_map + row) : row;
+          r[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(ep.resid + (size_t)grow * N + f0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
@@ -538,7 +541,8 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             x.x += bA.x; x.y += bA.y; x.z += bA.z; x.w += bA.w;
             if (ep.mode == EPI_RESID) { x.x += rs[i].x; x.y += rs[i].y; x.z += rs[i].z; x.w += rs[i].w; }
             else { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
-            if (row < M) *(reinterpret_cast<float4*>(out + (size_t)row * ld + f0) + c4) = x;
+            const int grow = (ep.row_map && row < M) ? __ldg(ep.row_map + row) : row;
+            if (row < M) *(reinterpret_cast<float4*>(out + (size_t)grow * ld + f0) + c4) = x;
           }
         } else {
 #pragma unroll

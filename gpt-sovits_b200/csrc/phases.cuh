@@ -820,10 +820,13 @@ __device__ bool sample_row(const Ctx& c, int r, int gstep, SampSmem& sm, int slo
     }
     const int step = gstep - step0;
     const int width = (step < c.eos_window) ? (V - 1) : V;
+    // test hooks: rows indexed by slot, or by utterance id (a recycled slot serves several utterances)
+    const int hstride = c.hook_rows > 0 ? c.hook_rows : c.B0;
+    const int hrow = c.hook_rows > 0 ? ((uid >= 0 && uid < c.hook_rows) ? uid : -1) : slot;
 #pragma unroll
     for (int j = 0; j < SV; ++j) {
       const int i = tid + NT * j;
-      if (c.logits_rec && step < c.n_logits_rec && i < V) c.logits_rec[((size_t)step * c.B0 + slot) * V + i] = v[j];
+      if (c.logits_rec && step < c.n_logits_rec && i < V && hrow >= 0) c.logits_rec[((size_t)step * hstride + hrow) * V + i] = v[j];
       if (i >= width) { valid[j] = false; v[j] = -INFINITY; }
     }
     // repetition penalty over every distinct previous token (prompt + generated), utils.py:159-167
@@ -887,8 +890,8 @@ __device__ bool sample_row(const Ctx& c, int r, int gstep, SampSmem& sm, int slo
     }
     // ---- bookkeeping (t2s_model.py:718-769)
     int emit = tok;
-    if (c.forced && step < c.n_forced) {
-      emit = __ldcg(c.forced + (size_t)slot * c.n_forced + step);
+    if (c.forced && step < c.n_forced && hrow >= 0) {
+      emit = __ldcg(c.forced + (size_t)hrow * c.n_forced + step);
       if (emit < 0 || emit >= V) {  // a forced id outside the embedding table: flag it and keep the reads in range
         if (tid == 0) atomicExch(c.abort_flag, ABORT_BAD_ID);
         emit = 0;

@@ -215,18 +215,23 @@ class T2SEngine:
         reserve_slots: int = 0,
         reserve_positions: int = 0,
         utt_ids: Optional[Sequence[int]] = None,
+        hooks_by_utterance: int = 0,
     ) -> InferResult:
         """phoneme_ids: B tensors [L_i] int64; bert: B tensors [1024, L_i]; prompt: [B, P] int64 or None.
         host_io=True takes CPU tensors and returns CPU tokens: the H2D / D2H copies happen inside the
         C-ABI call (bench.py's end-to-end leg).  reserve_slots / reserve_positions > 0 open the session with room for
         later ``admit()`` calls (continuous batching): that many slots in total, that many K/V positions per slot.
         utt_ids: one integer per utterance keying its Philox stream (default: its index in this call), so that sampling does not
-        depend on how a caller shards or batches the utterances."""
+        depend on how a caller shards or batches the utterances.  hooks_by_utterance = n > 0: the rows of ``forced`` / the captured
+        logits are indexed by utterance id (n rows) instead of by slot, so they follow an utterance through recycled slots."""
         rq, keep, B, P = self._request(phoneme_ids, bert, prompt, top_k, top_p, temperature, repetition_penalty, early_stop_num,
                                        eos_suppress_steps, max_steps, seed, host_io)
         ids, bert, prompt = keep
         dev = self.device
         cap = max(B, int(reserve_slots))
+        if hooks_by_utterance > 0:
+            cap = int(hooks_by_utterance)  # rows of the hook buffers
+        self.set_option(_lib.OPT_HOOKS_BY_UTTERANCE, int(hooks_by_utterance))
         self.set_option(_lib.OPT_SESSION_SLOTS, int(reserve_slots))
         self.set_option(_lib.OPT_SESSION_POSITIONS, int(reserve_positions))
         self._slot_P = [P] * B

@@ -195,8 +195,10 @@ enum {
   T2S_OPT_TC_DECODE_MIN_BATCH = 4, /* batch size from which decode projections run on tcgen05 (default 160, the measured crossover; 0: never) */
   T2S_OPT_SESSION_SLOTS = 5,     /* continuous batching: slots (utterances) the NEXT t2s_prefill reserves for the session, >= its own
                                     batch (0 = exactly its batch: no t2s_admit possible); the K/V pool is sized for all of them */
-  T2S_OPT_SESSION_POSITIONS = 6  /* K/V positions reserved per slot (0 = what the first request's longest utterance needs:
+  T2S_OPT_SESSION_POSITIONS = 6, /* K/V positions reserved per slot (0 = what the first request's longest utterance needs:
                                     phonemes + prompt + step cap); an admitted utterance must fit */
+  T2S_OPT_HOOKS_BY_UTTERANCE = 7 /* test hooks: 0 = forced tokens / captured logits are indexed by session slot; n > 0 = by utterance id
+                                    (t2s_set_utterance_ids), n rows - a recycled slot serves several utterances */
 };
 int t2s_set_option(t2s_engine* e, int32_t option, int64_t value);
 

@@ -441,8 +441,11 @@ def test_checkpoint_file_s1_v1_architecture_vs_reference(tmp_path, golden_dir, p
 
 def test_slot_reuse_serves_more_utterances_than_slots(golden_dir, pe_table):
     """A resident session with THREE slots serves the six utterances of the retire_b6 golden: a finished utterance's slot and K/V
-    pages are released and taken by the next admission (t2s_release_slots / t2s_admit).  Free-running greedy: every utterance
-    comes back with the (y, idx) the reference produced for it, whatever slot it decoded in and whenever it was admitted."""
+    pages are released and taken by the next admission (t2s_release_slots / t2s_admit).  Teacher-forced with the reference's
+    tokens BY UTTERANCE (T2S_OPT_HOOKS_BY_UTTERANCE: the hook rows follow an utterance through whatever slot it lands in), so
+    every utterance retires at the reference's step and EVERY step's logits - also those computed in a recycled slot, over K/V
+    pages a previous utterance used - are compared with the reference's, within the usual tolerance.  (Free-running greedy is not
+    a usable criterion here: all six trajectories of this golden meet a decision margin below 0.12 within their first five steps.)"""
     import gpt_sovits_b200 as gsb
     g = _golden(golden_dir, "retire_b6")
     sd = synthetic.make_state_dict(seed=int(g["weight_seed"]), eos_scale=float(g["eos_scale"]))
@@ -452,25 +455,40 @@ def test_slot_reuse_serves_more_utterances_than_slots(golden_dir, pe_table):
         ids, bert, prompt = _inputs(g)
         P = int(g["prompt_len"])
         ref_idx = [int(v) for v in g["idx"]]
+        n = g["logits"].shape[0]
+        forced = torch.zeros((6, n), dtype=torch.int32)
+        for b in range(6):
+            y = g["y"][b]
+            y = y[y >= 0][P:]
+            forced[b, : len(y)] = torch.from_numpy(y).to(torch.int32)
+            forced[b, ref_idx[b]] = 1024  # greedy reference: it stopped because its argmax was EOS
         sess = gsb.StreamingSession(eng, slots=3, positions=64 + P + 32, slice_steps=4, top_k=1, early_stop_num=int(g["early_stop_num"]),
-                                    eos_suppress_steps=1)
+                                    eos_suppress_steps=1, forced=forced, capture_logits=n, hooks_by_key=6)
         sess.submit(ids[:4], bert[:4], prompt[:4])
         got = {}
         for key, y, idx in sess:
             got[key] = (y.cpu().numpy(), idx)
-            if key == 0 or len(got) == 1:
-                sess.submit(ids[4:], bert[4:], prompt[4:]) if sess.n_submitted == 4 else None  # more text arrives while decoding
+            if sess.n_submitted == 4:
+                sess.submit(ids[4:], bert[4:], prompt[4:])  # more text arrives while decoding
         assert sorted(got) == list(range(6))
         assert len(eng._slot_P) == 3  # never more than three slots were in use: the others were recycled
-        same = 0
         for k in range(6):
             ref = g["y"][k]
             ref = ref[ref >= 0]
-            same += int(got[k][1] == ref_idx[k] and np.array_equal(got[k][0], ref))
-        print(f"slot reuse: 6 utterances through 3 slots, {same}/6 identical to the reference")
-        assert same >= 5  # (a near-tie step may leave the reference's greedy trajectory)
-        with pytest.raises(RuntimeError, match="already released|not in use|still decoding"):
-            eng.release([0, 0])
+            assert got[k][1] == ref_idx[k]
+            np.testing.assert_array_equal(got[k][0], ref)
+        # logits of every utterance's own steps 0 .. idx against the reference (the golden stores step s as [active list position])
+        mine = sess.first_logits.cpu().numpy()  # [n, 6 utterances, 1025], rows by utterance key
+        worst = 0.0
+        for st in range(n):
+            active = [b for b in range(6) if ref_idx[b] >= st]
+            w = 1024 if st < 1 else 1025
+            for pos, b in enumerate(active):
+                d = np.abs(mine[st, b, :w] - g["logits"][st, pos, :w]).max()
+                assert np.isfinite(d), (st, b)
+                worst = max(worst, float(d))
+        print(f"slot reuse: 6 utterances through 3 slots (teacher-forced by utterance), max |dlogit| vs reference = {worst:.4f}")
+        assert worst <= LOGIT_TOL
     finally:
         eng.close()
 
