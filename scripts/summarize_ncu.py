@@ -33,7 +33,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 import json
 for rep, title in (("prof_decode_b32", "k_decode_cluster: the bench workload's decode launch (B=32, 1000 steps in ONE launch of 7 clusters x 16 CTAs, mean KV 743) — `ncu --set full --clock-control none`"),
                    ("prof_gemm_b32", "k_gemm_tc<128> (tcgen05/TMEM + TMA prefill projections), B=32 (7755 rows) — `ncu --set full`"),
-                   ("prof_gemm_tcp_b32", "k_gemm_tcp<256> (round 2: persistent 128 x 256-tile tcgen05 GEMM), the four projections of one prefill layer (QKV, out_proj, linear1, linear2) at B=32 (7755 rows) — `ncu --set full`"),
+                   ("prof_gemm_tcp_b32", "k_gemm_tcp<256> (round 2: persistent 128 x 256-tile tcgen05 GEMM), four consecutive projections of the bench prefill (launches 40-43 of the call: linear2 of layer 9, then QKV, out_proj, linear1 of layer 10) at B=32 (7755 rows) — `ncu --set full`"),
                    ("prof_pattn_b32", "k_prefill_attn_tc (prefix-LM flash attention on mma.sync), B=32 — `ncu --set full`"),
                    ("prof_wide_b1", "k_decode_wide (round 2, mode 6: 144 CTAs, TMA weight ring, L2 {value, tag} hand-offs), batch 1, 300 steps in one launch — `ncu --set full`")):
     path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
