@@ -551,3 +551,27 @@ def test_utterance_ids_cover_a_chunked_call(engine, golden_dir):
         one = engine.infer([big_ids[j]], [big_bert[j]], big_prompt[j:j + 1], utt_ids=[500 + j], **kw)
         assert one.idx[0] == whole.idx[j]
         assert torch.equal(one.sequences()[0], whole.sequences()[j])
+
+
+def test_decode_beside_foreign_kernels(engine, golden_dir):
+    """The cluster-stream decode kernel spins on its own grid barrier and is not a cooperative launch: when another stream of the
+    process (SoVITS / the vocoder in the reference's pipeline; here back-to-back 8192^3 bf16 matmuls) holds SMs while it starts, its
+    clusters become resident as SMs free up and the call must neither trip the watchdog nor change its result - same request, same
+    batch composition, hence bit-identical tokens."""
+    g = _golden(golden_dir, "batch_b4")
+    ids, bert, prompt = _inputs(g)
+    kw = dict(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=200, eos_suppress_steps=1, seed=2024)
+    solo = engine.infer(ids, bert, prompt, **kw)
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device="cuda:0", dtype=torch.bfloat16)
+    with torch.cuda.stream(side):
+        for _ in range(150):  # ~100 ms of GEMMs that fill every SM, running before and during the decode launch
+            b = a @ a
+    busy = engine.infer(ids, bert, prompt, **kw)
+    still_running = not side.query()
+    torch.cuda.synchronize()
+    print(f"decode beside foreign kernels: side stream still busy when the call returned: {still_running}")
+    assert busy.idx == solo.idx
+    for x, y in zip(busy.sequences(), solo.sequences()):
+        assert torch.equal(x, y)
+    del b
