@@ -575,3 +575,40 @@ def test_decode_beside_foreign_kernels(engine, golden_dir):
     for x, y in zip(busy.sequences(), solo.sequences()):
         assert torch.equal(x, y)
     del b
+
+
+def test_two_engines_decode_from_two_threads(engine, weights_seed0, golden_dir, pe_table):
+    """Two engines in one process, driven from two threads at the same time (a server with a worker per voice): the persistent decode
+    kernels need every CTA co-resident, so the library serialises decode launches per process; both calls must return what they
+    return alone."""
+    import threading
+    import gpt_sovits_b200 as gsb
+    g = _golden(golden_dir, "batch_b4")
+    ids, bert, prompt = _inputs(g)
+    kw = dict(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, early_stop_num=120, eos_suppress_steps=1)
+    other = gsb.T2SEngine(synthetic.S1V2_CONFIG, device="cuda:0")
+    try:
+        other.load_state_dict(weights_seed0, pe=pe_table)
+        alone = [engine.infer(ids, bert, prompt, seed=5, **kw), other.infer(ids[:2], bert[:2], prompt[:2], seed=6, **kw)]
+        out, err = [None, None], []
+
+        def work(i, eng, args, seed):
+            try:
+                for _ in range(3):
+                    out[i] = eng.infer(*args, seed=seed, **kw)
+            except Exception as ex:  # noqa: BLE001
+                err.append(ex)
+
+        th = [threading.Thread(target=work, args=(0, engine, (ids, bert, prompt), 5)),
+              threading.Thread(target=work, args=(1, other, (ids[:2], bert[:2], prompt[:2]), 6))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not err, err
+        for i in range(2):
+            assert out[i].idx == alone[i].idx
+            for x, y in zip(out[i].sequences(), alone[i].sequences()):
+                assert torch.equal(x, y)
+    finally:
+        other.close()
