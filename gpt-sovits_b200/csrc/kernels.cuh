@@ -383,6 +383,9 @@ __global__ void __launch_bounds__(128) k_prefill_attn_tc(Ctx c, int layer, const
     for (int i = 0; i < 4; ++i) o[dt][i] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int mi = lane >> 3, r8 = lane & 7;  // ldmatrix: lane supplies row r8 of 8x8 matrix mi
+  int nv_min = min(nv0, nv1);              // keys every row of this warp sees (warp-uniform): tiles below it need no mask
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) nv_min = min(nv_min, __shfl_xor_sync(0xffffffffu, nv_min, o_));
   stage(0, 0);
   for (int kt = 0; kt < ntile; ++kt) {
     const int buf = kt & 1;
@@ -391,32 +394,44 @@ __global__ void __launch_bounds__(128) k_prefill_attn_tc(Ctx c, int layer, const
     __syncthreads();
     const unsigned char* kt_s = kv[buf];
     const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(kv[buf]) + 4096;
-    // ---- scores
+    // ---- scores: the B fragments of 8 keys x 32 dims (K rows as stored: b0 | b1 of k-block 0, b0 | b1 of k-block 1) come from ONE
+    //      ldmatrix.x4 (lane -> key r8 of the group, 16-byte chunk mi of its swizzled 64-byte row)
     float s[8][4];
+    const uint32_t kt_a = (uint32_t)__cvta_generic_to_shared(kt_s);
 #pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[n8][i] = 0.f;
-      const int key = n8 * 8 + g, sw = (key >> 1) & 3;
+      const int key = n8 * 8 + r8;
+      uint32_t b[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                   : "r"(kt_a + key * 64 + ((mi ^ ((key >> 1) & 3)) << 4)));
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kt_s + key * 64 + (((kb * 2) ^ sw) << 4) + t * 4);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kt_s + key * 64 + (((kb * 2 + 1) ^ sw) << 4) + t * 4);
-        mma_bf16_16816(s[n8], make_uint4(qh[kb][0], qh[kb][1], qh[kb][2], qh[kb][3]), b0, b1);
-        mma_bf16_16816(s[n8], make_uint4(ql[kb][0], ql[kb][1], ql[kb][2], ql[kb][3]), b0, b1);
+        mma_bf16_16816(s[n8], make_uint4(qh[kb][0], qh[kb][1], qh[kb][2], qh[kb][3]), b[2 * kb], b[2 * kb + 1]);
+        mma_bf16_16816(s[n8], make_uint4(ql[kb][0], ql[kb][1], ql[kb][2], ql[kb][3]), b[2 * kb], b[2 * kb + 1]);
       }
     }
-    // ---- mask + online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad)
+    // ---- mask + online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad).  A tile that every row of the warp
+    //      sees completely (all of it in front of the diagonal / inside the text block) needs no mask
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (kt * 64 + 64 <= nv_min) {
 #pragma unroll
-    for (int n8 = 0; n8 < 8; ++n8) {
-      const int j = kt * 64 + n8 * 8 + 2 * t;
-      if (j >= nv0) s[n8][0] = -INFINITY;
-      if (j + 1 >= nv0) s[n8][1] = -INFINITY;
-      if (j >= nv1) s[n8][2] = -INFINITY;
-      if (j + 1 >= nv1) s[n8][3] = -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(s[n8][0], s[n8][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[n8][2], s[n8][3]));
+      for (int n8 = 0; n8 < 8; ++n8) {
+        mx0 = fmaxf(mx0, fmaxf(s[n8][0], s[n8][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n8][2], s[n8][3]));
+      }
+    } else {
+#pragma unroll
+      for (int n8 = 0; n8 < 8; ++n8) {
+        const int j = kt * 64 + n8 * 8 + 2 * t;
+        if (j >= nv0) s[n8][0] = -INFINITY;
+        if (j + 1 >= nv0) s[n8][1] = -INFINITY;
+        if (j >= nv1) s[n8][2] = -INFINITY;
+        if (j + 1 >= nv1) s[n8][3] = -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[n8][0], s[n8][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n8][2], s[n8][3]));
+      }
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
