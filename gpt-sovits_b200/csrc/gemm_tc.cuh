@@ -287,18 +287,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 //   * a shared-memory operand ring that keeps running ACROSS tiles (the producer is up to STAGES k-blocks ahead, so the
 //     next tile's first operands land while the current tile's last MMAs run),
 //   * TWO accumulators in TMEM (2 x BN of the 512 columns): the MMAs of tile i+1 run while the epilogue drains tile i,
-//   * epilogue warps (TCP_EPI_WARPS / 4 per TMEM lane quarter, an equal share of the columns each) that re-stage every 32 x 32 fp32
-//     block through shared memory so that global reads (residual) and writes are 128-byte row segments instead of one 64-byte piece
-//     per thread and row (the non-persistent kernel's epilogue was LSU-bound: 32 different lines per store instruction); the
-//     loads of a block (bias, residual) are requested one block ahead.
-// Measured (scripts/mb_gemm.cu): the main loop alone runs at 1.25-1.4 PFLOP/s (2.1 us per K = 512 tile); with the
-// epilogue a tile takes ~7 us: SHARED MEMORY is the shared resource - per 128 x 256 tile 393 KB of TMA fill + 393 KB of operand
-// reads by the MMAs + 2 x 128 KB of staging = 1.04 MB against 128 B/clk, a 4.1 us floor - so the K = 512 projections run at
-// 0.45-0.75 PFLOP/s and only linear2 (K = 2048) reaches 1 PFLOP/s.  Built, measured and removed: a weight-stationary variant (a
-// CTA keeps one 128-column block of W in shared memory and streams only A: 0.81-0.84 PFLOP/s main loop, N = 128 MMAs read 128 B
-// of operands per clock, the whole shared-memory bandwidth); eight epilogue warps instead of four (no change); drain warps
-// (TMEM -> staging) and store warps (staging -> global) as separate roles with double-buffered staging (no change: the stores
-// alone sustain 21-26 B/clk per SM, scripts/mb_store.cu); bulk-copy stores from the staging block (slower).
+//   * four epilogue warps (one per TMEM lane quarter; tcgen05.ld 32x32b.x32: the thread holds 32 consecutive columns of ITS row)
+//     with two exits.  DIRECT (QKV, linear1): bias, q pre-scale / ReLU + bf16 pack / K/V-page swizzle in registers, then 256-bit
+//     stores, one whole 32-byte sector per lane.  STAGED (the residual projections out_proj, linear2, bert_proj): every 32 x 32
+//     fp32 block goes through a swizzled shared-memory block so that the residual loads and the stores are 128-byte row segments
+//     (the non-persistent kernel wrote one 64-byte piece per thread and row: 32 lines per store instruction); the loads of a
+//     block (bias, residual) are requested one block ahead.
+// Measured (scripts/mb_gemm.cu): the MMAs of a K = 512 tile are issued in 2.1 us, but SHARED MEMORY is the shared
+// resource - per 128 x 256 tile 393 KB of TMA fill + 393 KB of operand reads by the MMAs (+ 2 x 128 KB when the tile is staged)
+// against 128 B/clk: 3.1 us (4.1 us staged); the main loop alone runs at 3.5 us per tile (1.25-1.4 PFLOP/s).  Staged, every tile
+// drained in ~6.3 us; direct, bf16 tiles drain in 3.3-4 us and fp32 tiles in ~6 us (thread-per-row 256-bit stores sustain 15 B/clk
+// per SM, 128-byte segments 21-26: scripts/mb_store.cu).  Built, measured and removed: a weight-stationary variant (a CTA keeps one
+// 128-column block of W in shared memory and streams only A: 0.81-0.84 PFLOP/s main loop, N = 128 MMAs read 128 B of operands
+// per clock, the whole shared-memory bandwidth); eight epilogue warps instead of four (no change); drain warps (TMEM -> staging)
+// and store warps (staging -> global) as separate roles with double-buffered staging (no change); bulk-copy stores from the
+// staging block (slower).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2.. epilogue (TMEM lane quarter = warp % 4).
 // Epilogues: EPI_QKV, EPI_RESID, EPI_RELU (the three of T2SBlock.process_prompt, t2s_model.py:135-174).
 constexpr int TCP_EPI_WARPS = 4, TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;  // 8 (two per lane quarter) measured: no faster, and 204 registers spill
